@@ -1,0 +1,891 @@
+// capi.cu -- the C ABI of libcpm.so (declared in include/cpm.h): contexts, device-resident city /
+// fleet handles, and the host-pointer entry points that replace the reference's Julia functions.
+// No CPU fallback: every computing entry point launches the sm_100a kernels or fails.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cpm.h"
+#include "kernels.h"
+
+using namespace cpm;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int32_t fail(int32_t code, const char *fmt, const char *a = "", const char *b = "")
+{
+    char buf[512];
+    snprintf(buf, sizeof buf, fmt, a, b);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(e__ == cudaErrorMemoryAllocation ? CPM_ERR_OOM : CPM_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e__));                                                    \
+    } while (0)
+#define TRY(call)                                \
+    do {                                         \
+        int32_t r__ = (call);                    \
+        if (r__ != CPM_OK) return r__;           \
+    } while (0)
+#define ARG(cond)                                                             \
+    do {                                                                      \
+        if (!(cond)) return fail(CPM_ERR_ARG, "bad argument: %s", #cond);     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int32_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return CPM_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(CPM_ERR_OOM, "cudaMalloc(%s bytes): %s", std::to_string(bytes).c_str(), cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return CPM_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct cpm_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    // scratch objects of the host API (re-used across calls)
+    cpm_city *h_city = nullptr;
+    cpm_fleet *h_fleet = nullptr;
+    DevBuf traj_state, traj_trans, u[4], tmp, partials, scalars;
+    // optional timing of the sampling kernel: one event pair per day (consecutive launches of the step kernel)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;      // start0, stop0, start1, stop1, ...
+    std::vector<int64_t> ev_launches; // step-kernel launches bracketed by each pair
+};
+
+struct cpm_city {
+    cpm_ctx *ctx = nullptr;
+    int64_t N = 0, T = 0;
+    DevBuf dm, dist, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
+    bool have_inputs = false, have_meansum = false, have_pdrive = false, have_cdf = false, have_pdest = false;
+};
+
+struct cpm_fleet {
+    cpm_ctx *ctx = nullptr;
+    int64_t C = 0;
+    DevBuf zone, counts, time_partials, scalars, norm_out;
+    int64_t counts_N = 0, counts_steps = 0;   // shape of the last run's counts
+    int64_t car_offset = 0;
+};
+
+struct Scalars {   // device-side scalar block of a fleet
+    double time_sum;
+    unsigned long long lost;
+};
+
+static int32_t use(cpm_ctx *ctx)
+{
+    ARG(ctx != nullptr);
+    CU(cudaSetDevice(ctx->device));
+    return CPM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plumbing
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t cpm_version(void) { return CPM_VERSION; }
+extern "C" const char *cpm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t cpm_device_count(int32_t *count)
+{
+    ARG(count != nullptr);
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    *count = n;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_ctx_create(int32_t device, void *stream, cpm_ctx **out)
+{
+    ARG(out != nullptr);
+    *out = nullptr;
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (n <= 0) return fail(CPM_ERR_CUDA, "no CUDA device visible (libcpm has no CPU fallback)");
+    ARG(device >= 0 && device < n);
+    CU(cudaSetDevice(device));
+    cpm_ctx *c = new (std::nothrow) cpm_ctx();
+    if (!c) return fail(CPM_ERR_OOM, "host allocation failed");
+    c->device = device;
+    if (stream) { c->st = (cudaStream_t)stream; c->own_stream = false; }
+    else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return fail(CPM_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        c->own_stream = true;
+    }
+    *out = c;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
+{
+    if (!ctx) return CPM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    if (ctx->h_city) cpm_city_destroy(ctx->h_city);
+    if (ctx->h_fleet) cpm_fleet_destroy(ctx->h_fleet);
+    for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    ctx->traj_state.release(); ctx->traj_trans.release(); ctx->tmp.release(); ctx->partials.release(); ctx->scalars.release();
+    for (auto &b : ctx->u) b.release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->st);
+    delete ctx;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_ctx_sync(cpm_ctx *ctx)
+{
+    TRY(use(ctx));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_ctx_stream(cpm_ctx *ctx, void **stream_out)
+{
+    ARG(ctx && stream_out);
+    *stream_out = (void *)ctx->st;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_ctx_launch_count(cpm_ctx *ctx, int64_t *count)
+{
+    ARG(ctx && count);
+    *count = ctx->launches;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_host_alloc(int64_t bytes, void **out)
+{
+    ARG(out && bytes >= 0);
+    CU(cudaHostAlloc(out, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_host_free(void *p)
+{
+    if (p) CU(cudaFreeHost(p));
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_ctx_profile_begin(cpm_ctx *ctx)
+{
+    TRY(use(ctx));
+    for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    ctx->ev.clear(); ctx->ev_launches.clear();
+    ctx->profiling = true;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int64_t *step_launches)
+{
+    TRY(use(ctx));
+    ctx->profiling = false;
+    CU(cudaStreamSynchronize(ctx->st));
+    double ms = 0.0; int64_t n = 0;
+    for (size_t k = 0; k + 1 < ctx->ev.size(); k += 2) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, ctx->ev[k], ctx->ev[k + 1]));
+        ms += t; n += ctx->ev_launches[k / 2];
+    }
+    for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    ctx->ev.clear(); ctx->ev_launches.clear();
+    if (step_kernel_ms) *step_kernel_ms = ms;
+    if (step_launches) *step_launches = n;
+    return CPM_OK;
+}
+
+static int32_t check_launch(cpm_ctx *ctx, int n)
+{
+    ctx->launches += n;
+    CU(cudaGetLastError());
+    return CPM_OK;
+}
+#define LAUNCH(ctx, expr) TRY(check_launch((ctx), (expr)))
+
+// ------------------------------------------------------------------------------------------------
+// city
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t cpm_city_create(cpm_ctx *ctx, int64_t N, int64_t T, cpm_city **out)
+{
+    TRY(use(ctx));
+    ARG(out && N >= 1 && T >= 1 && N <= 0x7fffffff);
+    cpm_city *c = new (std::nothrow) cpm_city();
+    if (!c) return fail(CPM_ERR_OOM, "host allocation failed");
+    c->ctx = ctx; c->N = N; c->T = T;
+    *out = c;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_destroy(cpm_city *c)
+{
+    if (!c) return CPM_OK;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->st);
+    c->dm.release(); c->dist.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
+    c->norm.release(); c->cdf.release(); c->rowzero.release();
+    delete c;
+    return CPM_OK;
+}
+
+static int32_t city_alloc_inputs(cpm_city *c)
+{
+    const size_t NN = (size_t)c->N * c->N;
+    TRY(c->dm.ensure(NN * c->T * 2 * sizeof(double)));
+    TRY(c->dist.ensure(NN * sizeof(double)));
+    return CPM_OK;
+}
+static void city_invalidate(cpm_city *c) { c->have_meansum = c->have_pdrive = c->have_cdf = c->have_pdest = false; }
+
+extern "C" int32_t cpm_city_upload(cpm_city *c, const double *datamatrix, const double *distance_matrix_km)
+{
+    ARG(c && datamatrix && distance_matrix_km);
+    TRY(use(c->ctx));
+    TRY(city_alloc_inputs(c));
+    const size_t NN = (size_t)c->N * c->N;
+    CU(cudaMemcpyAsync(c->dm.p, datamatrix, NN * c->T * 2 * sizeof(double), cudaMemcpyHostToDevice, c->ctx->st));
+    CU(cudaMemcpyAsync(c->dist.p, distance_matrix_km, NN * sizeof(double), cudaMemcpyHostToDevice, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));   // the caller may reuse its host buffers
+    c->have_inputs = true;
+    city_invalidate(c);
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_synth(cpm_city *c, uint64_t seed, double density)
+{
+    ARG(c != nullptr);
+    TRY(use(c->ctx));
+    TRY(city_alloc_inputs(c));
+    LAUNCH(c->ctx, launch_synth_city(c->dm.as<double>(), c->dist.as<double>(), c->N, c->T, seed, density, c->ctx->st));
+    c->have_inputs = true;
+    city_invalidate(c);
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_download_inputs(cpm_city *c, double *datamatrix, double *distance_matrix_km)
+{
+    ARG(c != nullptr);
+    TRY(use(c->ctx));
+    if (!c->have_inputs) return fail(CPM_ERR_STATE, "city has no inputs");
+    const size_t NN = (size_t)c->N * c->N;
+    if (datamatrix) CU(cudaMemcpyAsync(datamatrix, c->dm.p, NN * c->T * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->ctx->st));
+    if (distance_matrix_km) CU(cudaMemcpyAsync(distance_matrix_km, c->dist.p, NN * sizeof(double), cudaMemcpyDeviceToHost, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    return CPM_OK;
+}
+
+static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, double e_drive)
+{
+    if (!c->have_inputs) return fail(CPM_ERR_STATE, "createpdrive needs the city inputs (upload or synth first)");
+    const size_t NT = (size_t)c->N * c->T;
+    TRY(c->mean_sum.ensure(NT * sizeof(double)));
+    TRY(c->p_drive.ensure(NT * sizeof(double)));
+    if (!c->have_meansum) {   // parameter-independent: cached across sweeps
+        LAUNCH(c->ctx, launch_pdrive_meansum(c->dm.as<double>(), c->dist.as<double>(), c->N, c->T, c->mean_sum.as<double>(), c->ctx->st));
+        c->have_meansum = true;
+    }
+    LAUNCH(c->ctx, launch_pdrive_finish(c->mean_sum.as<double>(), c->N, c->T, p_min, p_max, e_drive, c->p_drive.as<double>(), c->ctx->st));
+    c->have_pdrive = true;
+    return CPM_OK;
+}
+static int32_t city_alloc_cdf(cpm_city *c)
+{
+    const size_t NN = (size_t)c->N * c->N;
+    TRY(c->cdf.ensure(NN * c->T * sizeof(double)));
+    TRY(c->rowzero.ensure((size_t)c->N * c->T));
+    return CPM_OK;
+}
+static int32_t city_build_pdestin_async(cpm_city *c, double e_dest)
+{
+    if (!c->have_inputs) return fail(CPM_ERR_STATE, "createpdestin needs the city inputs (upload or synth first)");
+    const size_t NN = (size_t)c->N * c->N;
+    TRY(c->p_dest.ensure(NN * c->T * sizeof(double)));
+    TRY(c->norm.ensure((size_t)c->N * c->T * sizeof(double)));
+    TRY(city_alloc_cdf(c));
+    LAUNCH(c->ctx, launch_pdestin(c->dm.as<double>(), c->N, c->T, e_dest, c->p_dest.as<double>(), c->norm.as<double>(), c->ctx->st));
+    LAUNCH(c->ctx, launch_cdf_normalise(c->p_dest.as<double>(), c->norm.as<double>(), c->N, c->T, c->cdf.as<double>(),
+                                        c->rowzero.as<uint8_t>(), c->ctx->st));
+    c->have_cdf = true;
+    c->have_pdest = true;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_city_build_pdrive(cpm_city *c, double p_min, double p_max, double e_drive)
+{
+    ARG(c != nullptr);
+    TRY(use(c->ctx));
+    return city_build_pdrive_async(c, p_min, p_max, e_drive);
+}
+extern "C" int32_t cpm_city_build_pdestin(cpm_city *c, double e_dest, int32_t keep_p_dest)
+{
+    ARG(c != nullptr);
+    TRY(use(c->ctx));
+    TRY(city_build_pdestin_async(c, e_dest));
+    if (!keep_p_dest) {   // p_dest is only a stage of the CDF build; drop it when the caller does not need it
+        CU(cudaStreamSynchronize(c->ctx->st));
+        c->p_dest.release();
+        c->have_pdest = false;
+    }
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_set_pdrive(cpm_city *c, const double *p_drive)
+{
+    ARG(c && p_drive);
+    TRY(use(c->ctx));
+    const size_t NT = (size_t)c->N * c->T;
+    TRY(c->p_drive.ensure(NT * sizeof(double)));
+    CU(cudaMemcpyAsync(c->p_drive.p, p_drive, NT * sizeof(double), cudaMemcpyHostToDevice, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    c->have_pdrive = true;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_set_pdest(cpm_city *c, const double *p_dest)
+{
+    ARG(c && p_dest);
+    TRY(use(c->ctx));
+    const size_t NN = (size_t)c->N * c->N;
+    TRY(c->p_dest.ensure(NN * c->T * sizeof(double)));
+    TRY(city_alloc_cdf(c));
+    CU(cudaMemcpyAsync(c->p_dest.p, p_dest, NN * c->T * sizeof(double), cudaMemcpyHostToDevice, c->ctx->st));
+    LAUNCH(c->ctx, launch_cdf_from_pdest(c->p_dest.as<double>(), c->N, c->T, c->cdf.as<double>(), c->rowzero.as<uint8_t>(), c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    c->have_cdf = true;
+    c->have_pdest = true;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_get_pdrive(cpm_city *c, double *out)
+{
+    ARG(c && out);
+    TRY(use(c->ctx));
+    if (!c->have_pdrive) return fail(CPM_ERR_STATE, "p_drive has not been built");
+    CU(cudaMemcpyAsync(out, c->p_drive.p, (size_t)c->N * c->T * sizeof(double), cudaMemcpyDeviceToHost, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_get_pdest(cpm_city *c, double *out)
+{
+    ARG(c && out);
+    TRY(use(c->ctx));
+    if (!c->have_pdest) return fail(CPM_ERR_STATE, "p_dest is not resident (build with keep_p_dest=1)");
+    CU(cudaMemcpyAsync(out, c->p_dest.p, (size_t)c->N * c->N * c->T * sizeof(double), cudaMemcpyDeviceToHost, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_city_get_cdf(cpm_city *c, double *out)
+{
+    ARG(c && out);
+    TRY(use(c->ctx));
+    if (!c->have_cdf) return fail(CPM_ERR_STATE, "the CDF has not been built");
+    CU(cudaMemcpyAsync(out, c->cdf.p, (size_t)c->N * c->N * c->T * sizeof(double), cudaMemcpyDeviceToHost, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    return CPM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fleet
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t cpm_fleet_create(cpm_ctx *ctx, int64_t C, cpm_fleet **out)
+{
+    TRY(use(ctx));
+    ARG(out && C >= 1);
+    cpm_fleet *f = new (std::nothrow) cpm_fleet();
+    if (!f) return fail(CPM_ERR_OOM, "host allocation failed");
+    f->ctx = ctx; f->C = C;
+    int32_t r = f->zone.ensure((size_t)C * sizeof(int32_t));
+    if (r == CPM_OK) r = f->scalars.ensure(sizeof(Scalars));
+    if (r == CPM_OK) r = f->time_partials.ensure((size_t)sampler_grid(C) * sizeof(double));
+    if (r != CPM_OK) { f->zone.release(); f->scalars.release(); delete f; return r; }
+    cudaMemsetAsync(f->zone.p, 0, (size_t)C * sizeof(int32_t), ctx->st);
+    *out = f;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_fleet_destroy(cpm_fleet *f)
+{
+    if (!f) return CPM_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->st);
+    f->zone.release(); f->counts.release(); f->time_partials.release(); f->scalars.release(); f->norm_out.release();
+    delete f;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_fleet_init(cpm_fleet *f, int64_t cars_per_zone, int64_t car_offset)
+{
+    ARG(f && cars_per_zone >= 1 && car_offset >= 0);
+    TRY(use(f->ctx));
+    f->car_offset = car_offset;
+    LAUNCH(f->ctx, launch_fleet_init(f->zone.as<int32_t>(), f->C, cars_per_zone, car_offset, f->ctx->st));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_fleet_set_zones(cpm_fleet *f, const int64_t *zones)
+{
+    ARG(f && zones);
+    TRY(use(f->ctx));
+    cpm_ctx *ctx = f->ctx;
+    TRY(ctx->tmp.ensure((size_t)f->C * sizeof(int64_t)));
+    CU(cudaMemcpyAsync(ctx->tmp.p, zones, (size_t)f->C * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    LAUNCH(ctx, launch_i64_to_i32(ctx->tmp.as<int64_t>(), f->zone.as<int32_t>(), f->C, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_fleet_get_zones(cpm_fleet *f, int64_t *zones_out)
+{
+    ARG(f && zones_out);
+    TRY(use(f->ctx));
+    cpm_ctx *ctx = f->ctx;
+    TRY(ctx->tmp.ensure((size_t)f->C * sizeof(int64_t)));
+    LAUNCH(ctx, launch_i32_to_i64(f->zone.as<int32_t>(), ctx->tmp.as<int64_t>(), f->C, ctx->st));
+    CU(cudaMemcpyAsync(zones_out, ctx->tmp.p, (size_t)f->C * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src)
+{
+    ARG(dst && src && dst->C == src->C && dst->ctx == src->ctx);
+    TRY(use(dst->ctx));
+    CU(cudaMemcpyAsync(dst->zone.p, src->zone.p, (size_t)dst->C * sizeof(int32_t), cudaMemcpyDeviceToDevice, dst->ctx->st));
+    return CPM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the day loop
+// ------------------------------------------------------------------------------------------------
+struct Traj {
+    int64_t *state = nullptr;   // Julia layout [C,T]
+    double *trans = nullptr;    // Julia layout [C,T,4]
+    int64_t T = 0;
+    bool update_last = false;   // IVP writes state[:,t+1] for every step; resampling skips t = T
+};
+
+static RngDev make_rng(const cpm_rng &r, int64_t C)
+{
+    RngDev d;
+    d.mode = r.mode;
+    d.stream = r.stream;
+    d.k0 = (uint32_t)(r.seed & 0xffffffffu);
+    d.k1 = (uint32_t)(r.seed >> 32);
+    d.car_offset = r.car_offset;
+    d.ld = C;
+    d.u_drive = r.u_drive; d.u_dest = r.u_dest; d.u_time = r.u_time; d.u_dist = r.u_dist;
+    return d;
+}
+
+// Enqueues n_steps steps (no host sync).  Counts, driving-time sum and lost counter are reset first.
+static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj)
+{
+    cpm_ctx *ctx = f->ctx;
+    ARG(city->ctx == ctx);
+    ARG(o->n_steps >= 1 && o->steps_per_hour >= 1);
+    ARG((o->n_steps - 1) / o->steps_per_hour < city->T);
+    ARG(o->rng.mode == CPM_RNG_PHILOX || o->rng.mode == CPM_RNG_INJECTED);
+    ARG(o->sampler == CPM_SAMPLER_AUTO || o->sampler == CPM_SAMPLER_GATHER || o->sampler == CPM_SAMPLER_BUCKET);
+    if (!city->have_pdrive || !city->have_cdf) return fail(CPM_ERR_STATE, "sampling needs p_drive and the p_dest CDF (build or set them first)");
+    if (o->with_time && !city->have_inputs) return fail(CPM_ERR_STATE, "travel-time sampling needs datamatrix and distance_matrix_km");
+    if (o->rng.mode == CPM_RNG_INJECTED) {
+        ARG(o->rng.u_drive && o->rng.u_dest);
+        if (o->with_time) ARG(o->rng.u_time && o->rng.u_dist);
+    }
+    const int64_t N = city->N;
+    const size_t n_counts = (size_t)N * o->n_steps;
+    TRY(f->counts.ensure(2 * n_counts * sizeof(uint32_t)));
+    f->counts_N = N; f->counts_steps = o->n_steps;
+    const int grid = sampler_grid(f->C);
+    CU(cudaMemsetAsync(f->counts.p, 0, 2 * n_counts * sizeof(uint32_t), ctx->st));
+    CU(cudaMemsetAsync(f->time_partials.p, 0, (size_t)grid * sizeof(double), ctx->st));
+    CU(cudaMemsetAsync(f->scalars.p, 0, sizeof(Scalars), ctx->st));
+
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.p_drive = city->p_drive.as<double>();
+    a.cdf = city->cdf.as<double>();
+    a.rowzero = city->rowzero.as<uint8_t>();
+    a.dm = city->dm.as<double>();
+    a.dist = city->dist.as<double>();
+    a.N = N; a.T_tab = city->T;
+    a.zone = f->zone.as<int32_t>();
+    a.C = f->C;
+    a.with_time = o->with_time;
+    a.rng = make_rng(o->rng, f->C);
+    a.time_partials = f->time_partials.as<double>();
+    a.lost = &f->scalars.as<Scalars>()->lost;
+    if (traj) { a.traj_state = traj->state; a.traj_trans = traj->trans; a.T_traj = traj->T; }
+    if (ctx->profiling) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        ctx->ev.push_back(e0); ctx->ev.push_back(e1); ctx->ev_launches.push_back(o->n_steps);
+        CU(cudaEventRecord(e0, ctx->st));
+    }
+    for (int64_t s = 0; s < o->n_steps; ++s) {
+        a.step = s;
+        a.hour = s / o->steps_per_hour;
+        a.parking = f->counts.as<uint32_t>() + (size_t)N * s;
+        a.driving = f->counts.as<uint32_t>() + n_counts + (size_t)N * s;
+        if (traj) { a.t_traj = s; a.write_next_state = (s + 1 < traj->T) ? 1 : 0; }
+        LAUNCH(ctx, launch_step_gather(a, ctx->st));
+    }
+    if (ctx->profiling) CU(cudaEventRecord(ctx->ev.back(), ctx->st));
+    if (o->with_time)
+        LAUNCH(ctx, launch_reduce_partials(f->time_partials.as<double>(), grid, &f->scalars.as<Scalars>()->time_sum, ctx->st));
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_run_day(cpm_city *city, cpm_fleet *fleet, const cpm_day_opts *opts)
+{
+    ARG(city && fleet && opts);
+    TRY(use(fleet->ctx));
+    return run_day_async(city, fleet, opts, nullptr);
+}
+
+extern "C" int32_t cpm_fleet_get_counts(cpm_fleet *f, int64_t *parking, int64_t *driving, double *time_sum, int64_t *n_lost)
+{
+    ARG(f != nullptr);
+    TRY(use(f->ctx));
+    if (f->counts_steps == 0) return fail(CPM_ERR_STATE, "no day has been run on this fleet");
+    const size_t n = (size_t)f->counts_N * f->counts_steps;
+    std::vector<uint32_t> h(2 * n);
+    Scalars sc;
+    CU(cudaMemcpyAsync(h.data(), f->counts.p, 2 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, f->ctx->st));
+    CU(cudaMemcpyAsync(&sc, f->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, f->ctx->st));
+    CU(cudaStreamSynchronize(f->ctx->st));
+    if (parking) for (size_t k = 0; k < n; ++k) parking[k] = h[k];
+    if (driving) for (size_t k = 0; k < n; ++k) driving[k] = h[n + k];
+    if (time_sum) *time_sum = sc.time_sum;
+    if (n_lost) *n_lost = (int64_t)sc.lost;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_fleet_counts_device(cpm_fleet *f, void **dev_ptr, int64_t *n_elems)
+{
+    ARG(f && dev_ptr && n_elems);
+    if (f->counts_steps == 0) return fail(CPM_ERR_STATE, "no day has been run on this fleet");
+    *dev_ptr = f->counts.p;
+    *n_elems = 2 * f->counts_N * f->counts_steps;
+    return CPM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// main.jl:82-98 on the device
+// ------------------------------------------------------------------------------------------------
+struct NormOut {   // device layout of the normalised outputs of one day: parking[N*T], traffic[T], counts[T]
+    static size_t bytes(int64_t N, int64_t T) { return ((size_t)N * T + T) * sizeof(double) + (size_t)T * sizeof(unsigned long long); }
+};
+
+static int32_t normalise_async(cpm_fleet *f, int64_t N, int64_t T, int64_t C_total)
+{
+    TRY(f->norm_out.ensure(NormOut::bytes(N, T)));
+    double *parking = f->norm_out.as<double>();
+    double *traffic = parking + (size_t)N * T;
+    unsigned long long *tc = reinterpret_cast<unsigned long long *>(traffic + T);
+    const uint32_t *cp = f->counts.as<uint32_t>();
+    LAUNCH(f->ctx, launch_normalise_counts(cp, cp + (size_t)N * T, N, T, C_total, parking, nullptr, traffic, tc, f->ctx->st));
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cpm_params *pr, int64_t cars_per_zone,
+                                      uint64_t seed, int32_t sampler, double *parking, double *traffic, double *A_drive,
+                                      int64_t *n_lost)
+{
+    ARG(city && fleet && pr && cars_per_zone >= 1);
+    cpm_ctx *ctx = fleet->ctx;
+    TRY(use(ctx));
+    const int64_t N = city->N, T = city->T;
+    ARG(fleet->C == N * cars_per_zone);
+    TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive));                 // main.jl:82
+    TRY(city_build_pdestin_async(city, pr->e_dest));                                        // main.jl:85
+    LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->st));   // main.jl:88
+    fleet->car_offset = 0;
+    cpm_day_opts o;
+    memset(&o, 0, sizeof o);
+    o.steps_per_hour = 1; o.sampler = sampler;
+    o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
+    int64_t lost_ivp = 0;
+    if (T > 1) {
+        o.n_steps = T - 1; o.with_time = 0; o.rng.stream = 0;                               // main.jl:91-92
+        TRY(run_day_async(city, fleet, &o, nullptr));
+        if (n_lost) {
+            Scalars sc;
+            CU(cudaMemcpyAsync(&sc, fleet->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+            lost_ivp = (int64_t)sc.lost;
+        }
+    }
+    o.n_steps = T; o.with_time = 1; o.rng.stream = 1;                                       // main.jl:95
+    TRY(run_day_async(city, fleet, &o, nullptr));
+    TRY(normalise_async(fleet, N, T, fleet->C));                                            // saveresults.jl:6-28
+    const double *d_parking = fleet->norm_out.as<double>();
+    Scalars sc;
+    if (parking) CU(cudaMemcpyAsync(parking, d_parking, (size_t)N * T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    if (traffic) CU(cudaMemcpyAsync(traffic, d_parking + (size_t)N * T, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&sc, fleet->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (A_drive) *A_drive = sc.time_sum / ((double)fleet->C * (double)T * 60 * 60);         // averagedrivingtime.jl:10
+    if (n_lost) *n_lost = lost_ivp + (int64_t)sc.lost;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params, int64_t P,
+                             uint64_t seed, int32_t common_random_numbers, int64_t *traffic_counts, double *A_drive,
+                             double *parking)
+{
+    ARG(city && initial_zones && params && P >= 1 && C >= 1);
+    cpm_ctx *ctx = city->ctx;
+    TRY(use(ctx));
+    const int64_t N = city->N, T = city->T;
+    cpm_fleet *base = nullptr, *work = nullptr;
+    int32_t rc = cpm_fleet_create(ctx, C, &base);
+    if (rc == CPM_OK) rc = cpm_fleet_create(ctx, C, &work);
+    if (rc == CPM_OK) rc = cpm_fleet_set_zones(base, initial_zones);
+    std::vector<unsigned long long> tc((size_t)T);
+    bool have_e_dest = false;
+    double cur_e_dest = 0.0;
+    for (int64_t p = 0; rc == CPM_OK && p < P; ++p) {
+        const cpm_params &pr = params[p];
+        if (!have_e_dest || pr.e_dest != cur_e_dest || !city->have_cdf) {   // CDFs are shared by sets with equal e_dest
+            rc = city_build_pdestin_async(city, pr.e_dest);
+            have_e_dest = true; cur_e_dest = pr.e_dest;
+        }
+        if (rc == CPM_OK) rc = city_build_pdrive_async(city, pr.p_min, pr.p_max, pr.e_drive);   // mean_sum cached
+        if (rc == CPM_OK) rc = cpm_fleet_copy_zones(work, base);                                  // README.md:1014,1549
+        cpm_day_opts o;
+        memset(&o, 0, sizeof o);
+        o.n_steps = T; o.steps_per_hour = 1; o.with_time = 1; o.sampler = CPM_SAMPLER_AUTO;
+        o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
+        o.rng.stream = common_random_numbers ? 1u : (uint32_t)(2 + p);
+        if (rc == CPM_OK) rc = run_day_async(city, work, &o, nullptr);
+        if (rc == CPM_OK) rc = normalise_async(work, N, T, C);
+        if (rc != CPM_OK) break;
+        const double *d_parking = work->norm_out.as<double>();
+        const unsigned long long *d_tc = reinterpret_cast<const unsigned long long *>(d_parking + (size_t)N * T + T);
+        Scalars sc;
+        cudaError_t e = cudaMemcpyAsync(tc.data(), d_tc, (size_t)T * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&sc, work->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st);
+        if (e == cudaSuccess && parking)
+            e = cudaMemcpyAsync(parking + (size_t)N * T * p, d_parking, (size_t)N * T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+        if (e != cudaSuccess) { rc = fail(CPM_ERR_CUDA, "sweep copy-out: %s", cudaGetErrorString(e)); break; }
+        if (traffic_counts) for (int64_t t = 0; t < T; ++t) traffic_counts[t + T * p] = (int64_t)tc[(size_t)t];
+        if (A_drive) A_drive[p] = sc.time_sum / ((double)C * (double)T * 60 * 60);
+    }
+    cpm_fleet_destroy(base);
+    cpm_fleet_destroy(work);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host API: the reference's Julia functions with host pointers
+// ------------------------------------------------------------------------------------------------
+static int32_t host_city(cpm_ctx *ctx, int64_t N, int64_t T, cpm_city **out)
+{
+    if (ctx->h_city && (ctx->h_city->N != N || ctx->h_city->T != T)) { cpm_city_destroy(ctx->h_city); ctx->h_city = nullptr; }
+    if (!ctx->h_city) TRY(cpm_city_create(ctx, N, T, &ctx->h_city));
+    *out = ctx->h_city;
+    return CPM_OK;
+}
+static int32_t host_fleet(cpm_ctx *ctx, int64_t C, cpm_fleet **out)
+{
+    if (ctx->h_fleet && ctx->h_fleet->C != C) { cpm_fleet_destroy(ctx->h_fleet); ctx->h_fleet = nullptr; }
+    if (!ctx->h_fleet) TRY(cpm_fleet_create(ctx, C, &ctx->h_fleet));
+    *out = ctx->h_fleet;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_create_pdrive(cpm_ctx *ctx, const double *datamatrix, const double *distance_matrix_km, int64_t N,
+                                     int64_t T, double p_min, double p_max, double e_drive, double *p_drive_out)
+{
+    TRY(use(ctx));
+    ARG(datamatrix && distance_matrix_km && p_drive_out && N >= 1 && T >= 1);
+    cpm_city *c;
+    TRY(host_city(ctx, N, T, &c));
+    TRY(cpm_city_upload(c, datamatrix, distance_matrix_km));
+    TRY(city_build_pdrive_async(c, p_min, p_max, e_drive));
+    return cpm_city_get_pdrive(c, p_drive_out);
+}
+
+extern "C" int32_t cpm_create_pdestin(cpm_ctx *ctx, const double *datamatrix, int64_t N, int64_t T, double e_dest,
+                                      double *p_dest_out)
+{
+    TRY(use(ctx));
+    ARG(datamatrix && p_dest_out && N >= 1 && T >= 1);
+    cpm_city *c;
+    TRY(host_city(ctx, N, T, &c));
+    // only the mean slab [N,N,T,1] is read (src/createpdestin.jl:13,23)
+    TRY(city_alloc_inputs(c));
+    CU(cudaMemcpyAsync(c->dm.p, datamatrix, (size_t)N * N * T * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    const bool had_inputs = c->have_inputs;
+    c->have_inputs = true;
+    city_invalidate(c);
+    int32_t rc = city_build_pdestin_async(c, e_dest);
+    if (rc == CPM_OK) rc = cpm_city_get_pdest(c, p_dest_out);
+    c->have_inputs = false;   // std slab and distances were not uploaded: do not let later calls trust them
+    (void)had_inputs;
+    return rc;
+}
+
+extern "C" int32_t cpm_initialize_states(cpm_ctx *ctx, int64_t C, int64_t T, int64_t cars_per_zone, int64_t *state, double *trans)
+{
+    TRY(use(ctx));
+    ARG(state && trans && C >= 1 && T >= 1 && cars_per_zone >= 1);
+    const size_t CT = (size_t)C * T;
+    TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
+    TRY(ctx->traj_trans.ensure(CT * 4 * sizeof(double)));
+    LAUNCH(ctx, launch_init_states(ctx->traj_state.as<int64_t>(), ctx->traj_trans.as<double>(), C, T, cars_per_zone, ctx->st));
+    CU(cudaMemcpyAsync(state, ctx->traj_state.p, CT * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(trans, ctx->traj_trans.p, CT * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}
+
+// uploads injected variates (host -> device) and rewrites the rng to device pointers
+static int32_t stage_rng(cpm_ctx *ctx, const cpm_rng *in, int64_t C, int64_t n_steps, bool with_time, cpm_rng *out)
+{
+    *out = *in;
+    if (in->mode != CPM_RNG_INJECTED) return CPM_OK;
+    const double *src[4] = { in->u_drive, in->u_dest, in->u_time, in->u_dist };
+    const double **dst[4] = { &out->u_drive, &out->u_dest, &out->u_time, &out->u_dist };
+    const int n = with_time ? 4 : 2;
+    for (int k = 0; k < n; ++k) {
+        ARG(src[k] != nullptr);
+        const size_t bytes = (size_t)C * n_steps * sizeof(double);
+        TRY(ctx->u[k].ensure(bytes));
+        CU(cudaMemcpyAsync(ctx->u[k].p, src[k], bytes, cudaMemcpyHostToDevice, ctx->st));
+        *dst[k] = ctx->u[k].as<double>();
+    }
+    return CPM_OK;
+}
+
+static int32_t host_sample(cpm_ctx *ctx, int64_t *state, double *trans, const double *p_drive, const double *p_dest,
+                           const double *datamatrix, const double *distance_matrix_km, int64_t C, int64_t N, int64_t T,
+                           const cpm_rng *rng, bool ivp, int64_t *initial_state_out, int64_t *n_lost_out)
+{
+    ARG(state && trans && p_drive && p_dest && rng && C >= 1 && N >= 1 && T >= 1);
+    cpm_city *city; cpm_fleet *fleet;
+    TRY(host_city(ctx, N, T, &city));
+    TRY(host_fleet(ctx, C, &fleet));
+    if (!ivp) {
+        ARG(datamatrix && distance_matrix_km);
+        TRY(cpm_city_upload(city, datamatrix, distance_matrix_km));
+    }
+    TRY(cpm_city_set_pdrive(city, p_drive));
+    TRY(cpm_city_set_pdest(city, p_dest));
+    const size_t CT = (size_t)C * T;
+    TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
+    TRY(ctx->traj_trans.ensure(CT * 4 * sizeof(double)));
+    int64_t *d_state = ctx->traj_state.as<int64_t>();
+    double *d_trans = ctx->traj_trans.as<double>();
+    // column 1 of state_matrix is the only state input (src/resampling.jl:12 at t = 1)
+    CU(cudaMemcpyAsync(d_state, state, (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    LAUNCH(ctx, launch_i64_to_i32(d_state, fleet->zone.as<int32_t>(), C, ctx->st));
+    const int64_t n_steps = ivp ? T - 1 : T;
+    if (!ivp)   // slots 3-4 of non-driving cars keep their previous contents (src/resampling.jl:55-77)
+        CU(cudaMemcpyAsync(d_trans + 2 * CT, trans + 2 * CT, 2 * CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    if (n_steps >= 1) {
+        cpm_day_opts o;
+        memset(&o, 0, sizeof o);
+        o.n_steps = n_steps; o.steps_per_hour = 1; o.with_time = ivp ? 0 : 1; o.sampler = CPM_SAMPLER_GATHER;
+        TRY(stage_rng(ctx, rng, C, n_steps, !ivp, &o.rng));
+        Traj tj; tj.state = d_state; tj.trans = d_trans; tj.T = T;
+        TRY(run_day_async(city, fleet, &o, &tj));
+        // copy back exactly the blocks the reference writes
+        if (T > 1) CU(cudaMemcpyAsync(state + C, d_state + C, (size_t)C * (T - 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+        const size_t ncol = (size_t)C * n_steps;
+        CU(cudaMemcpyAsync(trans, d_trans, ncol * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(trans + CT, d_trans + CT, ncol * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+        if (!ivp) CU(cudaMemcpyAsync(trans + 2 * CT, d_trans + 2 * CT, 2 * CT * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    }
+    if (initial_state_out)   // state_matrix[:,24] (src/solveinitialvalueproblem.jl:57), generalised to column T
+        CU(cudaMemcpyAsync(initial_state_out, d_state + (size_t)C * (T - 1), (size_t)C * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
+    Scalars sc;
+    CU(cudaMemcpyAsync(&sc, fleet->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (n_lost_out) *n_lost_out = n_steps >= 1 ? (int64_t)sc.lost : 0;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_solve_ivp(cpm_ctx *ctx, int64_t *state, double *trans, const double *p_drive, const double *p_dest,
+                                 int64_t C, int64_t N, int64_t T, const cpm_rng *rng, int64_t *initial_state_out,
+                                 int64_t *n_lost_out)
+{
+    TRY(use(ctx));
+    ARG(initial_state_out != nullptr);
+    return host_sample(ctx, state, trans, p_drive, p_dest, nullptr, nullptr, C, N, T, rng, true, initial_state_out, n_lost_out);
+}
+
+extern "C" int32_t cpm_resampling(cpm_ctx *ctx, int64_t *state, double *trans, int64_t C, int64_t N, int64_t T,
+                                  const double *p_drive, const double *p_dest, const double *datamatrix,
+                                  const double *distance_matrix_km, const cpm_rng *rng, int64_t *n_lost_out)
+{
+    TRY(use(ctx));
+    return host_sample(ctx, state, trans, p_drive, p_dest, datamatrix, distance_matrix_km, C, N, T, rng, false, nullptr, n_lost_out);
+}
+
+extern "C" int32_t cpm_average_driving_time(cpm_ctx *ctx, int64_t C, int64_t T, double A_drive_in, const double *trans,
+                                            double *A_drive_out)
+{
+    TRY(use(ctx));
+    ARG(trans && A_drive_out && C >= 1 && T >= 1);
+    const size_t CT = (size_t)C * T;
+    TRY(ctx->tmp.ensure(CT * sizeof(double)));
+    const int np = sampler_grid((int64_t)CT);
+    TRY(ctx->partials.ensure((size_t)np * sizeof(double)));
+    TRY(ctx->scalars.ensure(sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->tmp.p, trans + 2 * CT, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 3
+    LAUNCH(ctx, launch_sum_f64(ctx->tmp.as<double>(), (int64_t)CT, ctx->partials.as<double>(), np, ctx->scalars.as<double>(), ctx->st));
+    double s = 0.0;
+    CU(cudaMemcpyAsync(&s, ctx->scalars.p, sizeof s, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    *A_drive_out = A_drive_in + s / ((double)C * (double)T * 60 * 60);   // :10
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_correct_parameters(double p_min_next, double p_max_next, double p_min, double p_max, double *out2)
+{
+    ARG(out2 != nullptr);
+    // four scalars of host arithmetic: src/correctparameters.jl:5-19
+    if (p_min_next < 0) p_min_next = 0;
+    else if (p_min_next > p_max) p_min_next = p_max;
+    if (p_max_next > 1) p_max_next = 1;
+    else if (p_max_next < p_min) p_max_next = p_min;
+    out2[0] = p_min_next;
+    out2[1] = p_max_next;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const double *trans, int64_t C, int64_t N, int64_t T,
+                                      double *parking, double *driving, double *traffic)
+{
+    TRY(use(ctx));
+    ARG(state && trans && C >= 1 && N >= 1 && T >= 1);
+    const size_t CT = (size_t)C * T, NT = (size_t)N * T;
+    TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
+    TRY(ctx->tmp.ensure(CT * sizeof(double)));
+    TRY(ctx->partials.ensure(2 * NT * sizeof(uint32_t) + (2 * NT + T) * sizeof(double)));
+    uint32_t *cnt = ctx->partials.as<uint32_t>();
+    double *outp = reinterpret_cast<double *>(cnt + 2 * NT);   // NT even multiples keep 8-byte alignment
+    CU(cudaMemcpyAsync(ctx->traj_state.p, state, CT * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->tmp.p, trans, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 1: drive flag
+    CU(cudaMemsetAsync(cnt, 0, 2 * NT * sizeof(uint32_t), ctx->st));
+    LAUNCH(ctx, launch_traj_histogram(ctx->traj_state.as<int64_t>(), ctx->tmp.as<double>(), C, N, T, cnt, cnt + NT, ctx->st));
+    LAUNCH(ctx, launch_normalise_counts(cnt, cnt + NT, N, T, C, outp, outp + NT, outp + 2 * NT, nullptr, ctx->st));
+    if (parking) CU(cudaMemcpyAsync(parking, outp, NT * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    if (driving) CU(cudaMemcpyAsync(driving, outp + NT, NT * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    if (traffic) CU(cudaMemcpyAsync(traffic, outp + 2 * NT, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}

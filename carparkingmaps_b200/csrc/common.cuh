@@ -1,0 +1,112 @@
+// common.cuh -- shared device helpers for libcpm (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cpm {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (car_lo, car_hi, step, 2*stream+phase),
+// key = (seed_lo, seed_hi).  Standard Random123 round constants; pinned by known-answer vectors in tests/.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 52-bit uniform on [0,1): the resolution of Julia <= 1.6 rand() (reference era).
+__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi)
+{
+    const uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 12) * 0x1.0p-52;
+}
+
+struct RngDev {
+    int32_t  mode;        // 0 philox, 1 injected
+    uint32_t stream;
+    uint32_t k0, k1;
+    int64_t  car_offset;
+    int64_t  ld;          // leading dimension (= C) of the injected arrays
+    const double *u_drive, *u_dest, *u_time, *u_dist;
+};
+
+// phase 0 -> (u_drive, u_dest); phase 1 -> (u_time, u_dist)
+__device__ __forceinline__ void philox_pair(const RngDev &r, int64_t car, uint32_t step, uint32_t phase,
+                                            double &ua, double &ub)
+{
+    const uint64_t g = (uint64_t)(r.car_offset + car);
+    uint32_t o[4];
+    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), step, r.stream * 2u + phase, r.k0, r.k1, o);
+    ua = u52(o[0], o[1]);
+    ub = u52(o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Julia semantics helpers
+// ---------------------------------------------------------------------------------------------
+// Float64 ^ e with Julia's Float64^Int fast paths (base/math.jl) for integral e in {-1,0,1,2,3}.
+__device__ __forceinline__ double jl_pow(double x, double e)
+{
+    if (e == 2.0) return x * x;
+    if (e == 1.0) return x;
+    if (e == 3.0) return x * x * x;
+    if (e == 0.0) return 1.0;
+    if (e == -1.0) return 1.0 / x;
+    return pow(x, e);
+}
+
+// Truncated(Normal(mu, sigma), 0.9mu, 1.1mu) by inverse CDF from one uniform (src/resampling.jl:68,74).
+// Symmetric interval: z = sqrt(2) * erfinv((2u-1) * erf(b/sqrt(2))), b = 0.1*mu/sigma.
+__device__ __forceinline__ double truncnormal(double mu, double sigma, double u)
+{
+    if (!(sigma > 0.0) || isinf(sigma) || isinf(mu) || isnan(mu)) return mu;
+    double lo = 0.9 * mu, hi = 1.1 * mu;
+    const double b = (0.1 * mu) / sigma;
+    const double E = erf(b / 1.41421356237309504880);
+    const double w = 2.0 * u - 1.0;
+    const double z = 1.41421356237309504880 * erfinv(w * E);
+    double x = mu + sigma * z;
+    if (lo > hi) { const double t = lo; lo = hi; hi = t; }
+    if (x < lo) x = lo;
+    if (x > hi) x = hi;
+    return x;
+}
+
+// Categorical draw on one CDF row (src/resampling.jl:38-45): first j (0-based) with
+// cdf[j-1] < u <= cdf[j] under a left-to-right running sum == lower_bound(u) on the sequential
+// fp64 CDF, then the acceptance test u <= cdf[j] (fails for u = 0 ... no: see below, NaN tails
+// and u above the last entry -> sentinel 0).  u == 0.0 never satisfies `range_low < u`, so it
+// also yields the sentinel.  Returns the 1-based destination or 0.
+template <typename LoadF>
+__device__ __forceinline__ int32_t cdf_search(LoadF load, int32_t n, double u)
+{
+    if (!(u > 0.0)) return 0;
+    int32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (load(mid) < u) lo = mid + 1; else hi = mid;   // NaN compares false -> goes left
+    }
+    if (lo >= n) return 0;
+    return (u <= load(lo)) ? lo + 1 : 0;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace cpm

@@ -1,0 +1,81 @@
+// kernels.h -- internal launcher interface between capi.cu and the kernel translation units.
+// All pointers are DEVICE pointers; every launcher enqueues on `st` and returns the number of
+// kernels it launched (summed into the context's launch counter).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace cpm {
+
+// ---- tables.cu --------------------------------------------------------------------------------
+// mean_sum[N,T] (src/createpdrive.jl:10-21)
+int launch_pdrive_meansum(const double *dm, const double *dist, int64_t N, int64_t T, double *mean_sum,
+                          cudaStream_t st);
+// p_drive[N,T] from mean_sum (src/createpdrive.jl:22-34)
+int launch_pdrive_finish(const double *mean_sum, int64_t N, int64_t T, double p_min, double p_max,
+                         double e_drive, double *p_drive, cudaStream_t st);
+// p_dest[N,N,T] (src/createpdestin.jl:3-50); norm is [N,T] scratch
+int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double *p_dest, double *norm,
+                   cudaStream_t st);
+// cdf[T][N][N] (destination fastest) + rowzero[T][N] from p_dest[N,N,T]: left-to-right fp64 running sum
+int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, uint8_t *rowzero,
+                          cudaStream_t st);
+
+// fused: p_dest /= norm (where norm > 0) and the CDF build in one pass (src/createpdestin.jl:38-46)
+int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, uint8_t *rowzero,
+                         cudaStream_t st);
+
+// ---- sampler.cu -------------------------------------------------------------------------------
+struct StepArgs {
+    // tables
+    const double *p_drive;   // [N,T]
+    const double *cdf;       // [T][N][N]
+    const uint8_t *rowzero;  // [T][N]
+    const double *dm;        // [N,N,T,2] (with_time only)
+    const double *dist;      // [N,N]     (with_time only)
+    int64_t N, T_tab;
+    // fleet
+    int32_t *zone;           // [C] 1-based, 0 = lost
+    int64_t C;
+    // step
+    int64_t step;            // rng step index
+    int64_t hour;            // table hour (0-based)
+    int32_t with_time;
+    RngDev rng;
+    // outputs
+    uint32_t *parking;       // [N] counts of this step (nullable)
+    uint32_t *driving;       // [N]
+    double *time_partials;   // [grid] per-block driving-time sums, accumulated over steps
+    unsigned long long *lost;// scalar
+    // trajectory in Julia layout (nullable): state Int64 [C,T_traj], trans Float64 [C,T_traj,4]
+    int64_t *traj_state;
+    double *traj_trans;
+    int64_t T_traj;
+    int64_t t_traj;          // column written by this step (0-based)
+    int32_t write_next_state;// state[:, t_traj+1] = destination
+};
+int sampler_grid(int64_t C);
+int launch_step_gather(const StepArgs &a, cudaStream_t st);
+int launch_reduce_partials(const double *partials, int n, double *out, cudaStream_t st);
+
+// helpers
+int launch_fleet_init(int32_t *zone, int64_t C, int64_t cars_per_zone, int64_t car_offset, cudaStream_t st);
+int launch_i64_to_i32(const int64_t *src, int32_t *dst, int64_t n, cudaStream_t st);
+int launch_i32_to_i64(const int32_t *src, int64_t *dst, int64_t n, cudaStream_t st);
+int launch_init_states(int64_t *state, double *trans, int64_t C, int64_t T, int64_t cars_per_zone, cudaStream_t st);
+// histogram of a Julia-layout trajectory (src/saveresults.jl:8-17)
+int launch_traj_histogram(const int64_t *state, const double *trans, int64_t C, int64_t N, int64_t T,
+                          uint32_t *parking, uint32_t *driving, cudaStream_t st);
+// sum of trans[:,:,3] (src/averagedrivingtime.jl:6-9): deterministic two-stage reduction
+int launch_sum_f64(const double *x, int64_t n, double *partials, int n_partials, double *out, cudaStream_t st);
+// parking = counts / C, traffic = minmax(colsum(driving)) (src/saveresults.jl:20-28)
+int launch_normalise_counts(const uint32_t *parking, const uint32_t *driving, int64_t N, int64_t T, int64_t C,
+                            double *parking_out, double *driving_out, double *traffic_out,
+                            unsigned long long *traffic_counts_out, cudaStream_t st);
+
+// ---- synth.cu ---------------------------------------------------------------------------------
+int launch_synth_city(double *dm, double *dist, int64_t N, int64_t T, uint64_t seed, double density,
+                      cudaStream_t st);
+
+}  // namespace cpm

@@ -1,0 +1,211 @@
+/*
+ * cpm.h -- C ABI of libcpm.so: the B200-native (sm_100a) implementation of the
+ * CarParkingMaps HMM sampling hot path.
+ *
+ * The reference (ArsamAryandoust/CarParkingMaps, Julia) has no FFI or plugin interface; its
+ * boundary is seven global Julia functions `include`d by main.jl:11-22 plus the globals they read
+ * (main.jl:37-42).  Each entry point below names the reference function it replaces (file:line,
+ * relative to the reference root).  A Julia host binds them with `ccall` (see INTEGRATION.md and
+ * carparkingmaps_b200/julia/CarParkingMapsGPU.jl); the Python mirror binds them with ctypes.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, scalars.  No C++/torch types.  No exceptions cross the ABI.
+ *   - Every function returns an int32 status (CPM_OK = 0); cpm_last_error() gives the message
+ *     of the last failure on the calling thread.
+ *   - Arrays use Julia's memory layout: dense, column-major (first index fastest), zone IDs are
+ *     1-based VALUES, state is Int64, everything else Float64.
+ *   - "Host API" functions take HOST pointers, are synchronous, and keep no host pointer after
+ *     they return.  "Engine API" functions work on device-resident handles (city / fleet) so a
+ *     pipeline can run without host round trips.
+ *   - There is no CPU fallback: every entry point that computes needs a CUDA device and fails
+ *     with CPM_ERR_CUDA otherwise.
+ */
+#ifndef CPM_H
+#define CPM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPM_VERSION 100
+
+enum {
+    CPM_OK = 0,
+    CPM_ERR_ARG = 1,     /* bad argument (null pointer, negative size, ...)              */
+    CPM_ERR_CUDA = 2,    /* CUDA runtime error, or no device                             */
+    CPM_ERR_OOM = 3,     /* device allocation failed                                     */
+    CPM_ERR_STATE = 4    /* call order violated (e.g. sampling before tables were built) */
+};
+
+/* Variate source.  The reference draws from Julia's unseeded global RNG
+ * (src/resampling.jl:13,29,68,74); here the source is explicit. */
+enum {
+    CPM_RNG_PHILOX = 0,  /* Philox4x32-10, counter = (car_lo, car_hi, step, 2*stream+phase),
+                            key = seed; phase 0 -> (u_drive,u_dest), phase 1 -> (u_time,u_dist);
+                            52-bit uniforms on [0,1) like Julia's rand()                     */
+    CPM_RNG_INJECTED = 1 /* u_*[i + C*t] supplied by the caller (parity testing)             */
+};
+
+typedef struct cpm_rng {
+    int32_t  mode;        /* CPM_RNG_*                                                   */
+    uint32_t stream;      /* philox stream id (distinct per IVP / day / trial)            */
+    uint64_t seed;        /* philox key                                                   */
+    int64_t  car_offset;  /* global 0-based index of local car 0 (car sharding over GPUs) */
+    const double *u_drive;/* injected: [C,n_steps] column-major                           */
+    const double *u_dest; /* injected: read only for driving cars                         */
+    const double *u_time; /* injected: read only for drivers with origin != destination   */
+    const double *u_dist; /* injected: idem                                               */
+} cpm_rng;
+
+typedef struct cpm_ctx cpm_ctx;     /* one per GPU; single caller at a time */
+typedef struct cpm_city cpm_city;   /* device-resident inputs + tables of one city/dataset */
+typedef struct cpm_fleet cpm_fleet; /* device-resident car state + per-zone counts */
+
+/* ---------------------------------------------------------------------------------------- */
+/* Plumbing                                                                                 */
+/* ---------------------------------------------------------------------------------------- */
+int32_t     cpm_version(void);
+const char *cpm_last_error(void);
+int32_t     cpm_device_count(int32_t *count);
+/* `stream` may be NULL (the context creates its own non-blocking stream) or an existing
+ * cudaStream_t, e.g. torch's current stream, so the caller's events bracket the kernels. */
+int32_t cpm_ctx_create(int32_t device, void *stream, cpm_ctx **out);
+int32_t cpm_ctx_destroy(cpm_ctx *ctx);
+int32_t cpm_ctx_sync(cpm_ctx *ctx);
+int32_t cpm_ctx_stream(cpm_ctx *ctx, void **stream_out);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+int32_t cpm_ctx_launch_count(cpm_ctx *ctx, int64_t *count);
+/* Times the sampling (step) kernel with CUDA events on the context's stream: between begin and end,
+ * every day loop is bracketed by one event pair around its consecutive step-kernel launches.
+ * end() synchronises and returns the summed device time and the number of launches it covers. */
+int32_t cpm_ctx_profile_begin(cpm_ctx *ctx);
+int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int64_t *step_launches);
+/* pinned host memory for callers that want full-rate PCIe copies */
+int32_t cpm_host_alloc(int64_t bytes, void **out);
+int32_t cpm_host_free(void *p);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Host API: one entry per reference function (HOST pointers, synchronous)                  */
+/* ---------------------------------------------------------------------------------------- */
+
+/* createpdrive(datamatrix, distance_matrix_km, number_zones) -- src/createpdrive.jl:3-38.
+ * The globals T, p_min, p_max, e_drive it reads (src/createpdrive.jl:4,31) are passed by value.
+ * datamatrix: [N,N,T,2], distance_matrix_km: [N,N], p_drive_out: [N,T]. */
+int32_t cpm_create_pdrive(cpm_ctx *ctx, const double *datamatrix, const double *distance_matrix_km,
+                          int64_t N, int64_t T, double p_min, double p_max, double e_drive,
+                          double *p_drive_out);
+
+/* createpdestin(datamatrix, number_zones) -- src/createpdestin.jl:3-50 (globals T, e_dest).
+ * p_dest_out: [N,N,T].  An integral e_dest in {-1,0,1,2,3} takes Julia's Float64^Int fast
+ * path (x*x for the reference's e_dest = 2, main.jl:38). */
+int32_t cpm_create_pdestin(cpm_ctx *ctx, const double *datamatrix, int64_t N, int64_t T,
+                           double e_dest, double *p_dest_out);
+
+/* initializestates(C) -- src/initializestates.jl:4-22 (globals T, cars_per_zone).
+ * state: Int64 [C,T], trans: Float64 [C,T,4]; both fully overwritten. */
+int32_t cpm_initialize_states(cpm_ctx *ctx, int64_t C, int64_t T, int64_t cars_per_zone,
+                              int64_t *state, double *trans);
+
+/* solveinitialvalueproblem(state_matrix, transition_matrix, p_drive, p_dest, C, number_zones)
+ * -- src/solveinitialvalueproblem.jl:4-62.  Mutates state[:,2:T], trans[:,1:T-1,1:2] in place
+ * exactly as the reference does and writes state[:,T] to initial_state_out [C].
+ * n_lost_out (nullable): number of (car,step) visits with zone 0 (see DESIGN.md "sentinel"). */
+int32_t cpm_solve_ivp(cpm_ctx *ctx, int64_t *state, double *trans, const double *p_drive,
+                      const double *p_dest, int64_t C, int64_t N, int64_t T, const cpm_rng *rng,
+                      int64_t *initial_state_out, int64_t *n_lost_out);
+
+/* resampling(state_matrix, transition_matrix, C, number_zones, p_drive, p_dest, datamatrix,
+ * distance_matrix_km) -- src/resampling.jl:3-89.  Mutates state[:,2:T] and trans in place; slots
+ * 3-4 of non-driving cars keep their previous contents, as in the reference. */
+int32_t cpm_resampling(cpm_ctx *ctx, int64_t *state, double *trans, int64_t C, int64_t N, int64_t T,
+                       const double *p_drive, const double *p_dest, const double *datamatrix,
+                       const double *distance_matrix_km, const cpm_rng *rng, int64_t *n_lost_out);
+
+/* averagedrivingtime(C, A_drive, transition_matrix) -- src/averagedrivingtime.jl:3-12. */
+int32_t cpm_average_driving_time(cpm_ctx *ctx, int64_t C, int64_t T, double A_drive_in,
+                                 const double *trans, double *A_drive_out);
+
+/* correctparameters(p_min_next, p_max_next, p_min, p_max) -- src/correctparameters.jl:3-23.
+ * out2 = {p_min_next, p_max_next}.  Pure host arithmetic (four scalars). */
+int32_t cpm_correct_parameters(double p_min_next, double p_max_next, double p_min, double p_max,
+                               double *out2);
+
+/* The per-zone histogram and normalisation inside saveresults -- src/saveresults.jl:6-28.
+ * parking: [N,T] = counts / C; driving: [N,T] raw counts; traffic: [T] min-max normalised
+ * column sums of driving.  Any output pointer may be NULL. */
+int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const double *trans, int64_t C,
+                           int64_t N, int64_t T, double *parking, double *driving, double *traffic);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Engine API: device-resident city tables and fleets                                       */
+/* ---------------------------------------------------------------------------------------- */
+int32_t cpm_city_create(cpm_ctx *ctx, int64_t N, int64_t T, cpm_city **out);
+int32_t cpm_city_destroy(cpm_city *city);
+/* inputs: either copied from host, or generated on the device (SURVEY 8d synthetic city) */
+int32_t cpm_city_upload(cpm_city *city, const double *datamatrix, const double *distance_matrix_km);
+int32_t cpm_city_synth(cpm_city *city, uint64_t seed, double density);
+int32_t cpm_city_download_inputs(cpm_city *city, double *datamatrix, double *distance_matrix_km);
+/* tables: built on the device from the inputs (createpdrive / createpdestin) ... */
+int32_t cpm_city_build_pdrive(cpm_city *city, double p_min, double p_max, double e_drive);
+int32_t cpm_city_build_pdestin(cpm_city *city, double e_dest, int32_t keep_p_dest);
+/* ... or supplied by the caller (the Julia API passes p_drive / p_dest as arguments) */
+int32_t cpm_city_set_pdrive(cpm_city *city, const double *p_drive);
+int32_t cpm_city_set_pdest(cpm_city *city, const double *p_dest);
+int32_t cpm_city_get_pdrive(cpm_city *city, double *p_drive_out);
+int32_t cpm_city_get_pdest(cpm_city *city, double *p_dest_out);       /* needs keep_p_dest */
+/* sampling CDF rows: [T][N origins][N destinations], destination fastest */
+int32_t cpm_city_get_cdf(cpm_city *city, double *cdf_out);
+
+int32_t cpm_fleet_create(cpm_ctx *ctx, int64_t C, cpm_fleet **out);
+int32_t cpm_fleet_destroy(cpm_fleet *fleet);
+/* car i (global index car_offset + i) starts in zone floor(i_global / cars_per_zone) + 1 */
+int32_t cpm_fleet_init(cpm_fleet *fleet, int64_t cars_per_zone, int64_t car_offset);
+int32_t cpm_fleet_set_zones(cpm_fleet *fleet, const int64_t *zones);
+int32_t cpm_fleet_get_zones(cpm_fleet *fleet, int64_t *zones_out);
+int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src);
+
+enum { CPM_SAMPLER_AUTO = 0, CPM_SAMPLER_GATHER = 1, CPM_SAMPLER_BUCKET = 2 };
+
+typedef struct cpm_day_opts {
+    int64_t n_steps;        /* steps to run (T-1 for the IVP, T for a resampling day)          */
+    int64_t steps_per_hour; /* table hour of step s is s / steps_per_hour (1 in the reference) */
+    int32_t with_time;      /* 0: phases 1-2 only (IVP); 1: also sample travel time/distance    */
+    int32_t sampler;        /* CPM_SAMPLER_*                                                    */
+    cpm_rng rng;            /* injected arrays are DEVICE pointers in the engine API            */
+} cpm_day_opts;
+
+/* Runs n_steps of the HMM on the fleet (counts-only: per-zone parked/driving counts per step,
+ * driving-time sum, lost-car visits are accumulated on the device). */
+int32_t cpm_run_day(cpm_city *city, cpm_fleet *fleet, const cpm_day_opts *opts);
+/* counts of the last cpm_run_day: parking/driving Int64 [N,n_steps]; any pointer may be NULL.
+ * These are raw per-rank counts: a multi-GPU host all-reduces them (SUM) before normalising. */
+int32_t cpm_fleet_get_counts(cpm_fleet *fleet, int64_t *parking, int64_t *driving,
+                             double *time_sum, int64_t *n_lost);
+/* device pointer to the uint32 [2][N,n_steps] count block (parking then driving), for an
+ * in-place NCCL all-reduce by the host when one city's cars are split over GPUs */
+int32_t cpm_fleet_counts_device(cpm_fleet *fleet, void **dev_ptr, int64_t *n_elems);
+
+/* main.jl:82-98 for one dataset, entirely on the device: build both tables, initialise C =
+ * N*cars_per_zone cars, solve the IVP, resample one day, reduce.  Outputs (host, nullable):
+ * parking [N,T] densities, traffic [T], A_drive increment (averagedrivingtime with A_drive_in=0). */
+typedef struct cpm_params {
+    double e_drive, e_dest, p_min, p_max;
+} cpm_params;
+int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cpm_params *params,
+                           int64_t cars_per_zone, uint64_t seed, int32_t sampler, double *parking,
+                           double *traffic, double *A_drive, int64_t *n_lost);
+
+/* Model-selection sweep (README.md:956-1316, 1435-1681, 1831-2278 as a batched grid): for each of
+ * P parameter sets, rebuild the table(s), restart from `initial_zones` and resample one day.
+ * Outputs (host): traffic_counts Int64 [T,P] raw driving totals per hour, A_drive [P],
+ * parking (nullable) Float64 [N,T,P] densities. */
+int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params,
+                  int64_t P, uint64_t seed, int32_t common_random_numbers, int64_t *traffic_counts,
+                  double *A_drive, double *parking);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPM_H */
