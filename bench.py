@@ -59,7 +59,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, cuda_index):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         try:
             import pynvml
             import torch
@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
             self.err = repr(e)
 
     def run(self):
-        while self.ok and not self._stop.is_set():
+        while self.ok and not self._halt.is_set():
             try:
                 self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
             time.sleep(0.01)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join(timeout=1)
         if not self.ok:

@@ -50,7 +50,11 @@ __global__ void __launch_bounds__(256) k_synth_city(double *__restrict__ dm, dou
     const double v0 = 30.0 + 30.0 * hashu(seed, 3, i, j, 0);
     const double amp = 0.3 + 0.9 * hashu(seed, 4, i, j, 0);
     const double phase = -1.0 + 2.0 * hashu(seed, 5, i, j, 0);
-    const double base = (d * 3600.0) / v0;
+    // free-flow time, clipped so that mean = base * c stays inside the 60..3600 s range of the real data
+    // (c < 2.4) without flattening any pair to a constant (a constant pair makes NaN table entries)
+    double base = (d * 3600.0) / v0;
+    if (base < 60.0) base = 60.0;
+    if (base > 1500.0) base = 1500.0;
     for (int64_t t = 0; t < T; ++t) {
         double mean = 0.0, sd = 0.0;
         const bool present = (i != j) && (density >= 1.0 || hashu(seed, 8, i, j, (uint64_t)t) < density);
@@ -59,8 +63,6 @@ __global__ void __launch_bounds__(256) k_synth_city(double *__restrict__ dm, dou
             const double c = 1.0 + amp * (bump(h - 8.0 - phase) + bump(h - 17.5 - phase)) +
                              0.15 * hashu(seed, 9, i, j, (uint64_t)t);
             mean = base * c;
-            if (mean < 60.0) mean = 60.0;
-            if (mean > 3600.0) mean = 3600.0;
             sd = mean * (0.05 + 0.55 * hashu(seed, 6, i, j, (uint64_t)t));
             if (hashu(seed, 7, i, j, (uint64_t)t) < 0.02) sd = 0.0;   // exercises src/resampling.jl:65-67
         }

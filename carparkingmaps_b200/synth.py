@@ -53,6 +53,8 @@ def synth_city(N: int, T: int = 24, seed: int = 0, density: float = 1.0):
     amp = 0.3 + 0.9 * hashu(seed, 4, i, j, z)
     phase = -1.0 + 2.0 * hashu(seed, 5, i, j, z)
     base = (d * 3600.0) / v0
+    base = np.where(base < 60.0, 60.0, base)      # keeps mean = base * c (c < 2.4) inside 60..3600 s without
+    base = np.where(base > 1500.0, 1500.0, base)  # flattening any pair to a constant (which would make NaN table entries)
     dm = np.zeros((N, N, T, 2), order="F")
     offdiag = ~np.eye(N, dtype=bool)
     for t in range(T):
@@ -63,8 +65,6 @@ def synth_city(N: int, T: int = 24, seed: int = 0, density: float = 1.0):
         h = float((t % 24) + 1)
         c = 1.0 + amp * (_bump(h - 8.0 - phase) + _bump(h - 17.5 - phase)) + 0.15 * hashu(seed, 9, i, j, tt)
         mean = base * c
-        mean = np.where(mean < 60.0, 60.0, mean)
-        mean = np.where(mean > 3600.0, 3600.0, mean)
         sd = mean * (0.05 + 0.55 * hashu(seed, 6, i, j, tt))
         sd = np.where(hashu(seed, 7, i, j, tt) < 0.02, 0.0, sd)
         dm[:, :, t, 0] = np.where(present, mean, 0.0)
