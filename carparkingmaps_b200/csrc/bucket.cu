@@ -1,0 +1,514 @@
+// bucket.cu -- the "bucket" sampler: cars are kept grouped by their current zone, one CTA work item = one
+// zone (or a chunk of a large zone), and the origin's fp64 CDF row is staged in shared memory with a TMA
+// bulk copy (cp.async.bulk + mbarrier), double-buffered across work items.
+//
+// Why (profiles/README.md r1a): with one thread per car in car-id order the 12-probe binary search is a chain
+// of dependent L2/HBM loads under divergence; grouping by origin turns it into shared-memory probes, reads
+// every CDF row once per step (the algorithmic table traffic), and makes the per-zone parked-car
+// histogram free (it IS the bucket size).  Results are identical to the gather sampler and to the reference
+// algorithm because every draw is keyed by (global car id, step), not by processing order.
+//
+// Per step:  k_bucket_sample  (phases 1-3 per car; per-item shared-memory histogram of destinations with
+//                              warp-aggregated atomics; one global atomic per (item, destination) reserves a
+//                              range in the destination bucket)
+//            k_bucket_scatter (prefix-sum of the new bucket sizes, cars move to their new bucket; block 0 also
+//                              writes the next step's work-item list)
+// Reference semantics: src/resampling.jl:11-83, src/solveinitialvalueproblem.jl:11-53, src/saveresults.jl:8-17.
+#include "kernels.h"
+
+namespace cpm {
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (PTX; sm_90+ instructions, compiled for sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory layout of k_bucket_sample
+// ------------------------------------------------------------------------------------------------
+struct SampleSmem {
+    double *row[2];
+    uint32_t *hist;
+    int32_t *dest_s;
+    uint16_t *rank_s;
+    uint16_t *srch_idx;
+    double *srch_u;
+    uint64_t *bar;
+    uint32_t *misc;   // [0] n_search, [1] n_drive
+};
+
+__host__ __device__ inline size_t sample_smem_bytes(int64_t N, int64_t ldc, int CH, int nbuf)
+{
+    size_t b = (size_t)nbuf * ldc * 8;          // rows (16-byte aligned by construction)
+    b += (size_t)CH * 8;                        // srch_u
+    b += ((size_t)(N + 1) * 4 + 15) / 16 * 16;  // hist
+    b += (size_t)CH * 4;                        // dest_s
+    b += (size_t)CH * 2 * 2;                    // rank_s, srch_idx
+    b += 64;                                    // barriers + misc
+    return b;
+}
+
+__device__ __forceinline__ SampleSmem carve(unsigned char *base, int64_t N, int64_t ldc, int CH, int nbuf)
+{
+    SampleSmem s;
+    unsigned char *p = base;
+    s.row[0] = reinterpret_cast<double *>(p);
+    s.row[1] = reinterpret_cast<double *>(p + (nbuf > 1 ? (size_t)ldc * 8 : 0));
+    p += (size_t)nbuf * ldc * 8;
+    s.srch_u = reinterpret_cast<double *>(p); p += (size_t)CH * 8;
+    s.hist = reinterpret_cast<uint32_t *>(p); p += ((size_t)(N + 1) * 4 + 15) / 16 * 16;
+    s.dest_s = reinterpret_cast<int32_t *>(p); p += (size_t)CH * 4;
+    s.rank_s = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
+    s.srch_idx = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
+    s.bar = reinterpret_cast<uint64_t *>(p); p += 16;
+    s.misc = reinterpret_cast<uint32_t *>(p);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bucket_sample
+// ------------------------------------------------------------------------------------------------
+template <int NBUF>
+__global__ void __launch_bounds__(kBucketThreads, 2) k_bucket_sample(const BucketArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int THREADS = kBucketThreads, CH = kBucketChunk, R = CH / THREADS;
+    const int64_t N = a.N, NN = a.N * a.N;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    SampleSmem s = carve(smem_raw, N, a.ldc, CH, NBUF);
+    const uint32_t row_bytes = (uint32_t)(((N * 8 + 15) / 16) * 16);
+    const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
+    const double *__restrict__ pd_t = a.p_drive + N * a.hour;
+    const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
+    const bool inj = a.rng.mode == 1;
+    const int64_t uoff = a.rng.ld * a.step;
+    const int n_items = *a.n_items;
+
+    if (tid == 0) {
+        mbar_init(&s.bar[0], 1);
+        mbar_init(&s.bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    uint32_t parity[2] = {0u, 0u};
+    int buf = 0;
+    int w = blockIdx.x;
+    if (w < n_items && tid == 0) {
+        const int4 it = __ldg(a.items + w);
+        if (it.x < N) {
+            mbar_expect_tx(&s.bar[0], row_bytes);
+            tma_bulk_g2s(s.row[0], cdf_t + (int64_t)it.x * a.ldc, row_bytes, &s.bar[0]);
+        }
+    }
+    unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
+
+    for (; w < n_items; w += gridDim.x) {
+        const int4 it = __ldg(a.items + w);   // x = bin (0..N-1 zone, N = lost), y = first slot, z = #cars
+        const int bin = it.x, lo = it.y, n = it.z;
+        const bool is_zone = bin < N;
+        // prefetch the next item's row into the other buffer (single-buffer variant: issued after phase B)
+        if (NBUF == 2 && tid == 0) {
+            const int wn = w + gridDim.x;
+            if (wn < n_items) {
+                const int4 nx = __ldg(a.items + wn);
+                if (nx.x < N) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&s.bar[buf ^ 1], row_bytes);
+                    tma_bulk_g2s(s.row[buf ^ 1], cdf_t + (int64_t)nx.x * a.ldc, row_bytes, &s.bar[buf ^ 1]);
+                }
+            }
+        }
+        for (int x = tid; x <= N; x += THREADS) s.hist[x] = 0u;
+        if (tid == 0) { s.misc[0] = 0u; s.misc[1] = 0u; }
+        __syncthreads();
+
+        const double pd = is_zone ? __ldg(pd_t + bin) : -1.0;
+        const bool rowzero = is_zone ? (rz_t[bin] != 0) : true;
+        unsigned n_drive_thread = 0;
+
+        // ---- phase A: Bernoulli drive decision for every car of the item (src/resampling.jl:11-22) ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = r * THREADS + tid;
+            const bool active = k < n;
+            bool drive = false;
+            double u2 = 0.0;
+            if (active && is_zone) {
+                const int64_t id = a.perm_cur[lo + k];
+                double u1;
+                if (inj) u1 = a.rng.u_drive[id + uoff];
+                else philox_pair(a.rng, id, (uint32_t)a.step, 0u, u1, u2);
+                drive = u1 <= pd;                                   // :15 (<=; NaN p_drive parks)
+                if (drive && inj && !rowzero) u2 = a.rng.u_dest[id + uoff];
+            }
+            n_drive_thread += drive ? 1u : 0u;
+            const bool search = drive && !rowzero;
+            const bool stay = active && !search;                    // parked, all-zero row (:35-36), or lost
+            if (a.with_time && drive && rowzero) t_hi += 300ull;    // origin == destination: 5 minutes (:58-59)
+            // stayers: rank inside the own-zone bin via one warp-aggregated shared atomic
+            const uint32_t m_stay = __ballot_sync(0xffffffffu, stay);
+            uint32_t base = 0;
+            if (m_stay && lane == (__ffs(m_stay) - 1)) base = atomicAdd(&s.hist[bin], (uint32_t)__popc(m_stay));
+            base = __shfl_sync(0xffffffffu, base, m_stay ? (__ffs(m_stay) - 1) : 0);
+            if (stay) { s.dest_s[k] = bin; s.rank_s[k] = (uint16_t)(base + __popc(m_stay & lt_mask)); }
+            // searchers: compact (slot, u_dest) so that phase B runs without idle lanes
+            const uint32_t m_s = __ballot_sync(0xffffffffu, search);
+            uint32_t off = 0;
+            if (m_s && lane == (__ffs(m_s) - 1)) off = atomicAdd(&s.misc[0], (uint32_t)__popc(m_s));
+            off = __shfl_sync(0xffffffffu, off, m_s ? (__ffs(m_s) - 1) : 0);
+            if (search) {
+                const uint32_t q = off + __popc(m_s & lt_mask);
+                s.srch_idx[q] = (uint16_t)k;
+                s.srch_u[q] = u2;
+            }
+        }
+        {
+            unsigned nd = n_drive_thread;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
+            if (lane == 0 && nd) atomicAdd(&s.misc[1], nd);
+        }
+        if (!is_zone) lost += (tid == 0) ? (unsigned long long)n : 0ull;
+        __syncthreads();
+
+        // ---- phase B: categorical destination from the staged CDF row (src/resampling.jl:26-49) ----
+        const int n_search = (int)s.misc[0];
+        if (is_zone) {
+            mbar_wait(&s.bar[buf], parity[buf]);
+            parity[buf] ^= 1u;
+            const double *row = s.row[buf];
+            for (int q = tid; q < n_search; q += THREADS) {
+                const int k = s.srch_idx[q];
+                const double u2 = s.srch_u[q];
+                const int32_t d = cdf_search([&](int32_t j) { return row[j]; }, (int32_t)N, u2);   // 1-based, 0 = none
+                const int dbin = d ? d - 1 : (int)N;
+                s.dest_s[k] = dbin;
+                s.rank_s[k] = (uint16_t)atomicAdd(&s.hist[dbin], 1u);
+                if (a.with_time) {                                   // src/resampling.jl:53-70 (time only: counts mode)
+                    if (dbin == bin) t_hi += 300ull;
+                    else if (d >= 1) {
+                        const int64_t id = a.perm_cur[lo + k];
+                        double u3, u4;
+                        if (inj) u3 = a.rng.u_time[id + uoff];
+                        else philox_pair(a.rng, id, (uint32_t)a.step, 1u, u3, u4);
+                        const int64_t od = (int64_t)bin + N * (int64_t)(d - 1);
+                        const double mean = __ldg(a.dm + od + NN * a.hour);
+                        double sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
+                        if (sd == 0.0) sd = 0.1 * mean;
+                        fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (NBUF == 1 && tid == 0) {   // single buffer: the row is free again, fetch the next item's row now
+            const int wn = w + gridDim.x;
+            if (wn < n_items) {
+                const int4 nx = __ldg(a.items + wn);
+                if (nx.x < N) {
+                    fence_proxy_async();
+                    mbar_expect_tx(&s.bar[0], row_bytes);
+                    tma_bulk_g2s(s.row[0], cdf_t + (int64_t)nx.x * a.ldc, row_bytes, &s.bar[0]);
+                }
+            }
+        }
+
+        // ---- phase C: reserve a range in every destination bucket (one global atomic per item x destination) ----
+        for (int x = tid; x <= N; x += THREADS) {
+            const uint32_t c = s.hist[x];
+            if (c) s.hist[x] = atomicAdd(a.cnt_next + x, c);
+        }
+        if (tid == 0 && is_zone && s.misc[1]) atomicAdd(a.drv + bin, s.misc[1]);   // src/saveresults.jl:13-15
+        __syncthreads();
+
+        // ---- phase D: destination bin and position inside it, per slot (coalesced) ----
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = r * THREADS + tid;
+            if (k < n) {
+                const int db = s.dest_s[k];
+                a.dest[lo + k] = db;
+                a.pos[lo + k] = s.hist[db] + s.rank_s[k];
+            }
+        }
+        __syncthreads();
+        if (NBUF == 2) buf ^= 1;
+    }
+
+    // driving-time and lost-car totals: integer block reduction, two global atomics per CTA
+    __shared__ unsigned long long red[3];
+    if (tid < 3) red[tid] = 0ull;
+    __syncthreads();
+    t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo); lost = warp_sum_u64(lost);
+    if (lane == 0) {
+        if (t_hi) atomicAdd(&red[0], t_hi);
+        if (t_lo) atomicAdd(&red[1], t_lo);
+        if (lost) atomicAdd(&red[2], lost);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
+        if (hi) atomicAdd(a.t_hi, hi);
+        if (lo32) atomicAdd(a.t_lo, lo32);
+        if (red[2]) atomicAdd(a.lost, red[2]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefix sum of bucket sizes + work-item list (device function shared by k_bucket_items and k_bucket_scatter)
+// ------------------------------------------------------------------------------------------------
+// exclusive block scan of v[0..n) in place (v in shared memory); returns the total.  blockDim.x <= 1024.
+__device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot /*[32]*/)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + nt - 1) / nt;
+    const int b = tid * per, e = min(b + per, n);
+    uint32_t sum = 0;
+    for (int k = b; k < e; ++k) sum += v[k];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = (lane < (nt + 31) / 32) ? warp_tot[lane] : 0u;
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += y;
+        }
+        warp_tot[lane] = ti - t;   // exclusive warp offsets
+        if (lane == 31) warp_tot[32] = ti;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[wid] + inc - sum;
+    for (int k = b; k < e; ++k) { const uint32_t c = v[k]; v[k] = run; run += c; }
+    __syncthreads();
+    return warp_tot[32];
+}
+
+// start[] (shared, NB+1 entries incl. total) must already hold the exclusive scan of cnt[]
+__device__ void write_items(const uint32_t *__restrict__ cnt, const uint32_t *start, uint32_t *itoff, uint32_t *warp_tot,
+                            int NB, int4 *__restrict__ items, int32_t *__restrict__ n_items)
+{
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) itoff[x] = (cnt[x] + kBucketChunk - 1) / kBucketChunk;
+    __syncthreads();
+    const uint32_t total = block_exclusive_scan(itoff, NB, warp_tot);
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) {
+        const uint32_t c = cnt[x];
+        uint32_t o = itoff[x];
+        for (uint32_t j = 0; j * kBucketChunk < c; ++j)
+            items[o + j] = make_int4(x, (int)(start[x] + j * kBucketChunk), (int)min((uint32_t)kBucketChunk, c - j * kBucketChunk), 0);
+    }
+    if (threadIdx.x == 0) *n_items = (int32_t)total;
+}
+
+// day start / stand-alone: start[] and the item list from cnt[]
+__global__ void __launch_bounds__(1024) k_bucket_items(const uint32_t *__restrict__ cnt, int NB, uint32_t *__restrict__ start_out,
+                                                       int4 *__restrict__ items, int32_t *__restrict__ n_items)
+{
+    extern __shared__ uint32_t sm[];   // start[NB] | itoff[NB] | warp_tot[33]
+    uint32_t *start = sm, *itoff = sm + NB, *warp_tot = sm + 2 * NB;
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) start[x] = cnt[x];
+    __syncthreads();
+    block_exclusive_scan(start, NB, warp_tot);
+    if (start_out) for (int x = threadIdx.x; x < NB; x += blockDim.x) start_out[x] = start[x];
+    write_items(cnt, start, itoff, warp_tot, NB, items, n_items);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_bucket_scatter: cars move to their destination bucket (state update, src/resampling.jl:81-83)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_bucket_scatter(const ScatterArgs a)
+{
+    extern __shared__ uint32_t sm[];   // start[NB] | itoff[NB] (block 0) | warp_tot[33]
+    const int NB = a.NB;
+    uint32_t *start = sm, *itoff = sm + NB, *warp_tot = sm + 2 * NB;
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) start[x] = a.cnt_next[x];
+    __syncthreads();
+    block_exclusive_scan(start, NB, warp_tot);
+    for (int64_t sl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sl < a.C; sl += (int64_t)gridDim.x * blockDim.x) {
+        const int db = a.dest[sl];
+        const int32_t id = a.perm_cur[sl];
+        a.perm_next[start[db] + a.pos[sl]] = id;
+        if (a.zone_out) a.zone_out[id] = (db < NB - 1) ? db + 1 : 0;   // last step: car-id indexed state
+    }
+    if (blockIdx.x == 0 && a.items) {
+        __syncthreads();
+        write_items(a.cnt_next, start, itoff, warp_tot, NB, a.items, a.n_items);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bucketize a car-id indexed zone array (day start) and its inverse
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int zone_bin(int32_t z, int NB) { return (z >= 1 && z < NB) ? z - 1 : NB - 1; }
+
+__global__ void __launch_bounds__(256) k_bucket_hist(const int32_t *__restrict__ zone, int64_t C, int NB, uint32_t *__restrict__ cnt)
+{
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < C; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool act = i < C;
+        const int b = act ? zone_bin(zone[i], NB) : -1;
+        const uint32_t grp = __match_any_sync(0xffffffffu, b);       // lanes with the same bin
+        if (act && (threadIdx.x & 31) == (__ffs(grp) - 1)) atomicAdd(cnt + b, (uint32_t)__popc(grp));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bucket_place(const int32_t *__restrict__ zone, int64_t C, int NB,
+                                                      const uint32_t *__restrict__ start, uint32_t *__restrict__ cursor,
+                                                      int32_t *__restrict__ perm)
+{
+    const uint32_t lt = (1u << (threadIdx.x & 31)) - 1u;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < C; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool act = i < C;
+        const int b = act ? zone_bin(zone[i], NB) : -1;
+        const uint32_t grp = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if (act && (threadIdx.x & 31) == leader) base = atomicAdd(cursor + b, (uint32_t)__popc(grp));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (act) perm[start[b] + base + __popc(grp & lt)] = (int32_t)i;
+    }
+}
+
+// fleet_init directly in bucketed form: car i sits in zone i/cpz + 1 -> perm = identity, cnt = histogram of that map
+__global__ void __launch_bounds__(256) k_bucket_init_sorted(int32_t *__restrict__ perm, int64_t C)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) perm[i] = (int32_t)i;
+}
+
+// counts in the public layout: parking/driving uint32 [N, n_steps] from the bucket arrays with stride NB = N + 1
+__global__ void k_bucket_export_counts(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ drv, int N, int64_t n_steps,
+                                       uint32_t *__restrict__ parking, uint32_t *__restrict__ driving)
+{
+    const int64_t n = (int64_t)N * n_steps;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = k / N, z = k % N;
+        parking[k] = cnt[s * (N + 1) + z];
+        driving[k] = drv[s * (N + 1) + z];
+    }
+}
+
+__global__ void k_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = (double)(*hi) + (double)(*lo) * (1.0 / 4294967296.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+bool bucket_supported(int64_t N, int64_t ldc, int *nbuf_out, size_t *smem_out)
+{
+    if (N + 1 > 65535) return false;
+    for (int nbuf = 2; nbuf >= 1; --nbuf) {
+        const size_t b = sample_smem_bytes(N, ldc, kBucketChunk, nbuf);
+        // two CTAs per SM need 2*b <= 227 KB; a single CTA may use up to 227 KB
+        if ((nbuf == 2 && b <= 113 * 1024) || (nbuf == 1 && b <= 227 * 1024) || (nbuf == 2 && b <= 227 * 1024 && false)) {
+            if (nbuf_out) *nbuf_out = nbuf;
+            if (smem_out) *smem_out = b;
+            return true;
+        }
+    }
+    return false;
+}
+
+int launch_bucket_sample(const BucketArgs &a, cudaStream_t st)
+{
+    int nbuf = 0; size_t smem = 0;
+    if (!bucket_supported(a.N, a.ldc, &nbuf, &smem)) return -1;
+    static bool attr_set[3] = {false, false, false};
+    if (nbuf == 2) {
+        if (!attr_set[2]) { cudaFuncSetAttribute(k_bucket_sample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[2] = true; }
+        k_bucket_sample<2><<<kSMs * 2, kBucketThreads, smem, st>>>(a);
+    } else {
+        if (!attr_set[1]) { cudaFuncSetAttribute(k_bucket_sample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
+        k_bucket_sample<1><<<kSMs * (smem <= 113 * 1024 ? 2 : 1), kBucketThreads, smem, st>>>(a);
+    }
+    return 1;
+}
+
+static size_t scan_smem(int NB) { return ((size_t)2 * NB + 40) * sizeof(uint32_t); }
+
+int launch_bucket_items(const uint32_t *cnt, int NB, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_bucket_items, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    k_bucket_items<<<1, 1024, scan_smem(NB), st>>>(cnt, NB, start_out, items, n_items);
+    return 1;
+}
+
+int launch_bucket_scatter(const ScatterArgs &a, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_bucket_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    int64_t blocks = (a.C + 1023) / 1024;
+    if (blocks > kSMs * 2) blocks = kSMs * 2;
+    k_bucket_scatter<<<(unsigned)blocks, 1024, scan_smem(a.NB), st>>>(a);
+    return 1;
+}
+
+int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
+                     int32_t *perm, int4 *items, int32_t *n_items, cudaStream_t st)
+{
+    cudaMemsetAsync(cnt0, 0, (size_t)NB * sizeof(uint32_t), st);
+    cudaMemsetAsync(cursor_tmp, 0, (size_t)NB * sizeof(uint32_t), st);
+    const int g = sampler_grid(C);
+    k_bucket_hist<<<g, 256, 0, st>>>(zone, C, NB, cnt0);
+    launch_bucket_items(cnt0, NB, start_tmp, items, n_items, st);
+    k_bucket_place<<<g, 256, 0, st>>>(zone, C, NB, start_tmp, cursor_tmp, perm);
+    return 3;
+}
+
+int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
+                                uint32_t *driving, cudaStream_t st)
+{
+    k_bucket_export_counts<<<sampler_grid((int64_t)N * n_steps), 256, 0, st>>>(cnt, drv, N, n_steps, parking, driving);
+    return 1;
+}
+
+int launch_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out, cudaStream_t st)
+{
+    k_finalize_time<<<1, 32, 0, st>>>(hi, lo, out);
+    return 1;
+}
+
+}  // namespace cpm

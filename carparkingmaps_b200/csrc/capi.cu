@@ -86,20 +86,28 @@ struct cpm_city {
     cpm_ctx *ctx = nullptr;
     int64_t N = 0, T = 0;
     DevBuf dm, dist, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
+    int64_t ldc = 0;   // CDF row stride in doubles: N rounded up to 16 (128-byte rows: TMA-aligned for any N)
     bool have_inputs = false, have_meansum = false, have_pdrive = false, have_cdf = false, have_pdest = false;
 };
 
 struct cpm_fleet {
     cpm_ctx *ctx = nullptr;
     int64_t C = 0;
-    DevBuf zone, counts, time_partials, scalars, norm_out;
+    DevBuf zone, counts, scalars, norm_out;
     int64_t counts_N = 0, counts_steps = 0;   // shape of the last run's counts
     int64_t car_offset = 0;
+    // two equivalent representations of the car state: zone[car] (gather sampler, host API) and cars
+    // grouped by zone bin (bucket sampler); each is rebuilt lazily from the other
+    bool zone_valid = true, bucket_valid = false;
+    int64_t bucket_N = 0;
+    int cur = 0;
+    DevBuf perm[2], dest, pos, bcnt, bdrv, cnt_cur, start_tmp, cursor_tmp, items, n_items;
 };
 
 struct Scalars {   // device-side scalar block of a fleet
     double time_sum;
     unsigned long long lost;
+    unsigned long long t_hi, t_lo;   // fixed-point driving-time sum: seconds, 2^-32 s
 };
 
 static int32_t use(cpm_ctx *ctx)
@@ -309,8 +317,8 @@ static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, 
 }
 static int32_t city_alloc_cdf(cpm_city *c)
 {
-    const size_t NN = (size_t)c->N * c->N;
-    TRY(c->cdf.ensure(NN * c->T * sizeof(double)));
+    c->ldc = (c->N + 15) / 16 * 16;
+    TRY(c->cdf.ensure((size_t)c->N * c->ldc * c->T * sizeof(double)));
     TRY(c->rowzero.ensure((size_t)c->N * c->T));
     return CPM_OK;
 }
@@ -323,7 +331,7 @@ static int32_t city_build_pdestin_async(cpm_city *c, double e_dest)
     TRY(city_alloc_cdf(c));
     LAUNCH(c->ctx, launch_pdestin(c->dm.as<double>(), c->N, c->T, e_dest, c->p_dest.as<double>(), c->norm.as<double>(), c->ctx->st));
     LAUNCH(c->ctx, launch_cdf_normalise(c->p_dest.as<double>(), c->norm.as<double>(), c->N, c->T, c->cdf.as<double>(),
-                                        c->rowzero.as<uint8_t>(), c->ctx->st));
+                                        c->ldc, c->rowzero.as<uint8_t>(), c->ctx->st));
     c->have_cdf = true;
     c->have_pdest = true;
     return CPM_OK;
@@ -366,7 +374,7 @@ extern "C" int32_t cpm_city_set_pdest(cpm_city *c, const double *p_dest)
     TRY(c->p_dest.ensure(NN * c->T * sizeof(double)));
     TRY(city_alloc_cdf(c));
     CU(cudaMemcpyAsync(c->p_dest.p, p_dest, NN * c->T * sizeof(double), cudaMemcpyHostToDevice, c->ctx->st));
-    LAUNCH(c->ctx, launch_cdf_from_pdest(c->p_dest.as<double>(), c->N, c->T, c->cdf.as<double>(), c->rowzero.as<uint8_t>(), c->ctx->st));
+    LAUNCH(c->ctx, launch_cdf_from_pdest(c->p_dest.as<double>(), c->N, c->T, c->cdf.as<double>(), c->ldc, c->rowzero.as<uint8_t>(), c->ctx->st));
     CU(cudaStreamSynchronize(c->ctx->st));
     c->have_cdf = true;
     c->have_pdest = true;
@@ -395,7 +403,9 @@ extern "C" int32_t cpm_city_get_cdf(cpm_city *c, double *out)
     ARG(c && out);
     TRY(use(c->ctx));
     if (!c->have_cdf) return fail(CPM_ERR_STATE, "the CDF has not been built");
-    CU(cudaMemcpyAsync(out, c->cdf.p, (size_t)c->N * c->N * c->T * sizeof(double), cudaMemcpyDeviceToHost, c->ctx->st));
+    // device rows are padded to ldc doubles; the caller gets dense [T][N][N]
+    CU(cudaMemcpy2DAsync(out, (size_t)c->N * sizeof(double), c->cdf.p, (size_t)c->ldc * sizeof(double),
+                         (size_t)c->N * sizeof(double), (size_t)c->N * c->T, cudaMemcpyDeviceToHost, c->ctx->st));
     CU(cudaStreamSynchronize(c->ctx->st));
     return CPM_OK;
 }
@@ -406,13 +416,12 @@ extern "C" int32_t cpm_city_get_cdf(cpm_city *c, double *out)
 extern "C" int32_t cpm_fleet_create(cpm_ctx *ctx, int64_t C, cpm_fleet **out)
 {
     TRY(use(ctx));
-    ARG(out && C >= 1);
+    ARG(out && C >= 1 && C <= 0x7fffffff);
     cpm_fleet *f = new (std::nothrow) cpm_fleet();
     if (!f) return fail(CPM_ERR_OOM, "host allocation failed");
     f->ctx = ctx; f->C = C;
     int32_t r = f->zone.ensure((size_t)C * sizeof(int32_t));
     if (r == CPM_OK) r = f->scalars.ensure(sizeof(Scalars));
-    if (r == CPM_OK) r = f->time_partials.ensure((size_t)sampler_grid(C) * sizeof(double));
     if (r != CPM_OK) { f->zone.release(); f->scalars.release(); delete f; return r; }
     cudaMemsetAsync(f->zone.p, 0, (size_t)C * sizeof(int32_t), ctx->st);
     *out = f;
@@ -423,7 +432,9 @@ extern "C" int32_t cpm_fleet_destroy(cpm_fleet *f)
     if (!f) return CPM_OK;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->st);
-    f->zone.release(); f->counts.release(); f->time_partials.release(); f->scalars.release(); f->norm_out.release();
+    DevBuf *bufs[] = { &f->zone, &f->counts, &f->scalars, &f->norm_out, &f->perm[0], &f->perm[1], &f->dest, &f->pos, &f->bcnt,
+                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->items, &f->n_items };
+    for (DevBuf *b : bufs) b->release();
     delete f;
     return CPM_OK;
 }
@@ -433,6 +444,7 @@ extern "C" int32_t cpm_fleet_init(cpm_fleet *f, int64_t cars_per_zone, int64_t c
     TRY(use(f->ctx));
     f->car_offset = car_offset;
     LAUNCH(f->ctx, launch_fleet_init(f->zone.as<int32_t>(), f->C, cars_per_zone, car_offset, f->ctx->st));
+    f->zone_valid = true; f->bucket_valid = false;
     return CPM_OK;
 }
 extern "C" int32_t cpm_fleet_set_zones(cpm_fleet *f, const int64_t *zones)
@@ -444,6 +456,7 @@ extern "C" int32_t cpm_fleet_set_zones(cpm_fleet *f, const int64_t *zones)
     CU(cudaMemcpyAsync(ctx->tmp.p, zones, (size_t)f->C * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     LAUNCH(ctx, launch_i64_to_i32(ctx->tmp.as<int64_t>(), f->zone.as<int32_t>(), f->C, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    f->zone_valid = true; f->bucket_valid = false;
     return CPM_OK;
 }
 extern "C" int32_t cpm_fleet_get_zones(cpm_fleet *f, int64_t *zones_out)
@@ -451,6 +464,7 @@ extern "C" int32_t cpm_fleet_get_zones(cpm_fleet *f, int64_t *zones_out)
     ARG(f && zones_out);
     TRY(use(f->ctx));
     cpm_ctx *ctx = f->ctx;
+    if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
     TRY(ctx->tmp.ensure((size_t)f->C * sizeof(int64_t)));
     LAUNCH(ctx, launch_i32_to_i64(f->zone.as<int32_t>(), ctx->tmp.as<int64_t>(), f->C, ctx->st));
     CU(cudaMemcpyAsync(zones_out, ctx->tmp.p, (size_t)f->C * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
@@ -461,7 +475,9 @@ extern "C" int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src)
 {
     ARG(dst && src && dst->C == src->C && dst->ctx == src->ctx);
     TRY(use(dst->ctx));
+    if (!src->zone_valid) return fail(CPM_ERR_STATE, "source fleet zones are not materialised");
     CU(cudaMemcpyAsync(dst->zone.p, src->zone.p, (size_t)dst->C * sizeof(int32_t), cudaMemcpyDeviceToDevice, dst->ctx->st));
+    dst->zone_valid = true; dst->bucket_valid = false;
     return CPM_OK;
 }
 
@@ -472,7 +488,6 @@ struct Traj {
     int64_t *state = nullptr;   // Julia layout [C,T]
     double *trans = nullptr;    // Julia layout [C,T,4]
     int64_t T = 0;
-    bool update_last = false;   // IVP writes state[:,t+1] for every step; resampling skips t = T
 };
 
 static RngDev make_rng(const cpm_rng &r, int64_t C)
@@ -488,6 +503,118 @@ static RngDev make_rng(const cpm_rng &r, int64_t C)
     return d;
 }
 
+static int32_t profile_open(cpm_ctx *ctx, int64_t launches)
+{
+    if (!ctx->profiling) return CPM_OK;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    ctx->ev.push_back(e0); ctx->ev.push_back(e1); ctx->ev_launches.push_back(launches);
+    CU(cudaEventRecord(e0, ctx->st));
+    return CPM_OK;
+}
+static int32_t profile_close(cpm_ctx *ctx)
+{
+    if (ctx->profiling) CU(cudaEventRecord(ctx->ev.back(), ctx->st));
+    return CPM_OK;
+}
+
+// gather sampler: one thread per car, car-id order (also the only path that records trajectories)
+static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj)
+{
+    cpm_ctx *ctx = f->ctx;
+    const int64_t N = city->N;
+    const size_t n_counts = (size_t)N * o->n_steps;
+    if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
+    CU(cudaMemsetAsync(f->counts.p, 0, 2 * n_counts * sizeof(uint32_t), ctx->st));
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.p_drive = city->p_drive.as<double>();
+    a.cdf = city->cdf.as<double>();
+    a.ldc = city->ldc;
+    a.rowzero = city->rowzero.as<uint8_t>();
+    a.dm = city->dm.as<double>();
+    a.dist = city->dist.as<double>();
+    a.N = N; a.T_tab = city->T;
+    a.zone = f->zone.as<int32_t>();
+    a.C = f->C;
+    a.with_time = o->with_time;
+    a.rng = make_rng(o->rng, f->C);
+    Scalars *sc = f->scalars.as<Scalars>();
+    a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo; a.lost = &sc->lost;
+    if (traj) { a.traj_state = traj->state; a.traj_trans = traj->trans; a.T_traj = traj->T; }
+    TRY(profile_open(ctx, o->n_steps));
+    for (int64_t s = 0; s < o->n_steps; ++s) {
+        a.step = s;
+        a.hour = s / o->steps_per_hour;
+        a.parking = f->counts.as<uint32_t>() + (size_t)N * s;
+        a.driving = f->counts.as<uint32_t>() + n_counts + (size_t)N * s;
+        if (traj) { a.t_traj = s; a.write_next_state = (s + 1 < traj->T) ? 1 : 0; }
+        LAUNCH(ctx, launch_step_gather(a, ctx->st));
+    }
+    TRY(profile_close(ctx));
+    f->bucket_valid = false;
+    return CPM_OK;
+}
+
+// bucket sampler: cars grouped by zone, CDF rows staged in shared memory (bucket.cu)
+static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
+{
+    cpm_ctx *ctx = f->ctx;
+    const int64_t N = city->N, C = f->C;
+    const int NB = (int)N + 1;
+    const int64_t S = o->n_steps;
+    const size_t max_items = (size_t)NB + (size_t)(C / kBucketChunk) + 2;
+    TRY(f->perm[0].ensure((size_t)C * 4)); TRY(f->perm[1].ensure((size_t)C * 4));
+    TRY(f->dest.ensure((size_t)C * 4)); TRY(f->pos.ensure((size_t)C * 4));
+    TRY(f->bcnt.ensure((size_t)(S + 1) * NB * 4)); TRY(f->bdrv.ensure((size_t)S * NB * 4));
+    TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)NB * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
+    TRY(f->items.ensure(max_items * sizeof(int4))); TRY(f->n_items.ensure(16));
+    uint32_t *bcnt = f->bcnt.as<uint32_t>(), *bdrv = f->bdrv.as<uint32_t>();
+    CU(cudaMemsetAsync(bcnt, 0, (size_t)(S + 1) * NB * 4, ctx->st));
+    CU(cudaMemsetAsync(bdrv, 0, (size_t)S * NB * 4, ctx->st));
+    if (f->bucket_valid && f->bucket_N == N) {
+        // still grouped from the previous day: bucket sizes and the work-item list are current
+        CU(cudaMemcpyAsync(bcnt, f->cnt_cur.p, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    } else {
+        if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
+        f->cur = 0;
+        LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), C, NB, bcnt, f->start_tmp.as<uint32_t>(), f->cursor_tmp.as<uint32_t>(),
+                                     f->perm[0].as<int32_t>(), f->items.as<int4>(), f->n_items.as<int32_t>(), ctx->st));
+    }
+    Scalars *sc = f->scalars.as<Scalars>();
+    BucketArgs a;
+    memset(&a, 0, sizeof a);
+    a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc;
+    a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
+    a.N = N; a.T_tab = city->T; a.C = C;
+    a.dest = f->dest.as<int32_t>(); a.pos = f->pos.as<uint32_t>();
+    a.with_time = o->with_time;
+    a.rng = make_rng(o->rng, C);
+    a.items = f->items.as<int4>(); a.n_items = f->n_items.as<int32_t>();
+    a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo; a.lost = &sc->lost;
+    ScatterArgs sa;
+    memset(&sa, 0, sizeof sa);
+    sa.NB = NB; sa.dest = a.dest; sa.pos = a.pos; sa.C = C;
+    sa.items = f->items.as<int4>(); sa.n_items = f->n_items.as<int32_t>();
+    TRY(profile_open(ctx, S));
+    for (int64_t s = 0; s < S; ++s) {
+        a.step = s; a.hour = s / o->steps_per_hour;
+        a.perm_cur = f->perm[f->cur].as<int32_t>();
+        a.cnt_next = bcnt + (size_t)(s + 1) * NB;
+        a.drv = bdrv + (size_t)s * NB;
+        LAUNCH(ctx, launch_bucket_sample(a, ctx->st));
+        sa.cnt_next = a.cnt_next; sa.perm_cur = a.perm_cur; sa.perm_next = f->perm[f->cur ^ 1].as<int32_t>();
+        sa.zone_out = (s == S - 1) ? f->zone.as<int32_t>() : nullptr;
+        LAUNCH(ctx, launch_bucket_scatter(sa, ctx->st));
+        f->cur ^= 1;
+    }
+    TRY(profile_close(ctx));
+    CU(cudaMemcpyAsync(f->cnt_cur.p, bcnt + (size_t)S * NB, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    LAUNCH(ctx, launch_bucket_export_counts(bcnt, bdrv, (int)N, S, f->counts.as<uint32_t>(), f->counts.as<uint32_t>() + (size_t)N * S, ctx->st));
+    f->bucket_valid = true; f->bucket_N = N; f->zone_valid = true;
+    return CPM_OK;
+}
+
 // Enqueues n_steps steps (no host sync).  Counts, driving-time sum and lost counter are reset first.
 static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj)
 {
@@ -501,49 +628,19 @@ static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o
     if (o->with_time && !city->have_inputs) return fail(CPM_ERR_STATE, "travel-time sampling needs datamatrix and distance_matrix_km");
     if (o->rng.mode == CPM_RNG_INJECTED) {
         ARG(o->rng.u_drive && o->rng.u_dest);
-        if (o->with_time) ARG(o->rng.u_time && o->rng.u_dist);
+        if (o->with_time) ARG(o->rng.u_time && (traj == nullptr || o->rng.u_dist));
     }
     const int64_t N = city->N;
-    const size_t n_counts = (size_t)N * o->n_steps;
-    TRY(f->counts.ensure(2 * n_counts * sizeof(uint32_t)));
+    const bool can_bucket = traj == nullptr && bucket_supported(N, city->ldc, nullptr, nullptr);
+    if (o->sampler == CPM_SAMPLER_BUCKET && !can_bucket)
+        return fail(CPM_ERR_ARG, "the bucket sampler needs N + 1 <= 65535, a CDF row that fits shared memory, and no trajectory recording");
+    const bool use_bucket = can_bucket && o->sampler != CPM_SAMPLER_GATHER;
+    TRY(f->counts.ensure(2 * (size_t)N * o->n_steps * sizeof(uint32_t)));
     f->counts_N = N; f->counts_steps = o->n_steps;
-    const int grid = sampler_grid(f->C);
-    CU(cudaMemsetAsync(f->counts.p, 0, 2 * n_counts * sizeof(uint32_t), ctx->st));
-    CU(cudaMemsetAsync(f->time_partials.p, 0, (size_t)grid * sizeof(double), ctx->st));
     CU(cudaMemsetAsync(f->scalars.p, 0, sizeof(Scalars), ctx->st));
-
-    StepArgs a;
-    memset(&a, 0, sizeof a);
-    a.p_drive = city->p_drive.as<double>();
-    a.cdf = city->cdf.as<double>();
-    a.rowzero = city->rowzero.as<uint8_t>();
-    a.dm = city->dm.as<double>();
-    a.dist = city->dist.as<double>();
-    a.N = N; a.T_tab = city->T;
-    a.zone = f->zone.as<int32_t>();
-    a.C = f->C;
-    a.with_time = o->with_time;
-    a.rng = make_rng(o->rng, f->C);
-    a.time_partials = f->time_partials.as<double>();
-    a.lost = &f->scalars.as<Scalars>()->lost;
-    if (traj) { a.traj_state = traj->state; a.traj_trans = traj->trans; a.T_traj = traj->T; }
-    if (ctx->profiling) {
-        cudaEvent_t e0, e1;
-        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-        ctx->ev.push_back(e0); ctx->ev.push_back(e1); ctx->ev_launches.push_back(o->n_steps);
-        CU(cudaEventRecord(e0, ctx->st));
-    }
-    for (int64_t s = 0; s < o->n_steps; ++s) {
-        a.step = s;
-        a.hour = s / o->steps_per_hour;
-        a.parking = f->counts.as<uint32_t>() + (size_t)N * s;
-        a.driving = f->counts.as<uint32_t>() + n_counts + (size_t)N * s;
-        if (traj) { a.t_traj = s; a.write_next_state = (s + 1 < traj->T) ? 1 : 0; }
-        LAUNCH(ctx, launch_step_gather(a, ctx->st));
-    }
-    if (ctx->profiling) CU(cudaEventRecord(ctx->ev.back(), ctx->st));
-    if (o->with_time)
-        LAUNCH(ctx, launch_reduce_partials(f->time_partials.as<double>(), grid, &f->scalars.as<Scalars>()->time_sum, ctx->st));
+    TRY(use_bucket ? day_bucket(city, f, o) : day_gather(city, f, o, traj));
+    Scalars *sc = f->scalars.as<Scalars>();
+    if (o->with_time) LAUNCH(ctx, launch_finalize_time(&sc->t_hi, &sc->t_lo, &sc->time_sum, ctx->st));
     return CPM_OK;
 }
 

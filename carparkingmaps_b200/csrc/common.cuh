@@ -84,11 +84,12 @@ __device__ __forceinline__ double truncnormal(double mu, double sigma, double u)
     return x;
 }
 
-// Categorical draw on one CDF row (src/resampling.jl:38-45): first j (0-based) with
-// cdf[j-1] < u <= cdf[j] under a left-to-right running sum == lower_bound(u) on the sequential
-// fp64 CDF, then the acceptance test u <= cdf[j] (fails for u = 0 ... no: see below, NaN tails
-// and u above the last entry -> sentinel 0).  u == 0.0 never satisfies `range_low < u`, so it
-// also yields the sentinel.  Returns the 1-based destination or 0.
+// Categorical draw on one CDF row (src/resampling.jl:38-45).  The reference scans j = 1..N with a running
+// fp64 sum and takes the first j with range_low < u <= range_up.  On the same left-to-right running sum that
+// is lower_bound(u) followed by the acceptance test u <= cdf[j]: the test fails (sentinel 0, :32) when u lies
+// above the last entry or the running sum has turned NaN (`cdf < u` is false for NaN, so the search goes left
+// and stays correct on the finite prefix); u == 0.0 never satisfies `range_low < u` and also yields 0.
+// Returns the 1-based destination or 0.
 template <typename LoadF>
 __device__ __forceinline__ int32_t cdf_search(LoadF load, int32_t n, double u)
 {
@@ -100,6 +101,23 @@ __device__ __forceinline__ int32_t cdf_search(LoadF load, int32_t n, double u)
     }
     if (lo >= n) return 0;
     return (u <= load(lo)) ? lo + 1 : 0;
+}
+
+// Fixed-point driving-time accumulator: whole seconds in `hi`, 2^-32 s units in `lo`.  Integer adds commute,
+// so the sum is bit-reproducible for any processing order, grid shape, sampler or GPU split.
+__device__ __forceinline__ void fx_add(unsigned long long &hi, unsigned long long &lo, double x)
+{
+    if (!(x >= 0.0) || !(x < 9.0e15)) return;   // NaN / negative / absurd: not accumulated (cannot come from valid tables)
+    const double f = floor(x);
+    hi += (unsigned long long)f;
+    lo += (unsigned long long)rint((x - f) * 4294967296.0);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 __device__ __forceinline__ double warp_sum(double v)

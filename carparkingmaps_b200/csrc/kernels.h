@@ -19,18 +19,19 @@ int launch_pdrive_finish(const double *mean_sum, int64_t N, int64_t T, double p_
 int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double *p_dest, double *norm,
                    cudaStream_t st);
 // cdf[T][N][N] (destination fastest) + rowzero[T][N] from p_dest[N,N,T]: left-to-right fp64 running sum
-int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, uint8_t *rowzero,
+int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, uint8_t *rowzero,
                           cudaStream_t st);
 
 // fused: p_dest /= norm (where norm > 0) and the CDF build in one pass (src/createpdestin.jl:38-46)
-int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, uint8_t *rowzero,
-                         cudaStream_t st);
+int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc,
+                         uint8_t *rowzero, cudaStream_t st);
 
 // ---- sampler.cu -------------------------------------------------------------------------------
 struct StepArgs {
     // tables
     const double *p_drive;   // [N,T]
-    const double *cdf;       // [T][N][N]
+    const double *cdf;       // [T][N][ldc] destination fastest, rows padded to ldc (multiple of 16) doubles
+    int64_t ldc;
     const uint8_t *rowzero;  // [T][N]
     const double *dm;        // [N,N,T,2] (with_time only)
     const double *dist;      // [N,N]     (with_time only)
@@ -46,7 +47,7 @@ struct StepArgs {
     // outputs
     uint32_t *parking;       // [N] counts of this step (nullable)
     uint32_t *driving;       // [N]
-    double *time_partials;   // [grid] per-block driving-time sums, accumulated over steps
+    unsigned long long *t_hi, *t_lo;   // fixed-point driving-time sum (seconds, 2^-32 s)
     unsigned long long *lost;// scalar
     // trajectory in Julia layout (nullable): state Int64 [C,T_traj], trans Float64 [C,T_traj,4]
     int64_t *traj_state;
@@ -58,6 +59,40 @@ struct StepArgs {
 int sampler_grid(int64_t C);
 int launch_step_gather(const StepArgs &a, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int n, double *out, cudaStream_t st);
+
+// ---- bucket.cu --------------------------------------------------------------------------------
+constexpr int kBucketThreads = 512;
+constexpr int kBucketChunk = 2048;   // cars per work item (one zone, or a chunk of a large zone)
+struct BucketArgs {
+    const double *p_drive; const double *cdf; int64_t ldc; const uint8_t *rowzero; const double *dm;
+    int64_t N, T_tab;
+    const int32_t *perm_cur;   // [C] car ids grouped by zone bin
+    int32_t *dest;             // [C] destination bin per slot (N = lost)
+    uint32_t *pos;             // [C] position inside the destination bucket
+    int64_t C, step, hour;
+    int32_t with_time;
+    RngDev rng;
+    uint32_t *cnt_next;        // [N+1] bucket sizes of step+1 (accumulated)
+    uint32_t *drv;             // [N+1] driving cars per origin of this step
+    const int4 *items;         // (bin, first slot, #cars, -)
+    const int32_t *n_items;
+    unsigned long long *t_hi, *t_lo, *lost;
+};
+struct ScatterArgs {
+    const uint32_t *cnt_next; int NB;
+    const int32_t *dest; const uint32_t *pos; const int32_t *perm_cur; int32_t *perm_next; int64_t C;
+    int32_t *zone_out;         // nullable: car-id indexed zone (written on the last step of a day)
+    int4 *items; int32_t *n_items;   // next step's work items (written by block 0)
+};
+bool bucket_supported(int64_t N, int64_t ldc, int *nbuf_out, size_t *smem_out);
+int launch_bucket_sample(const BucketArgs &a, cudaStream_t st);
+int launch_bucket_scatter(const ScatterArgs &a, cudaStream_t st);
+int launch_bucket_items(const uint32_t *cnt, int NB, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st);
+int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
+                     int32_t *perm, int4 *items, int32_t *n_items, cudaStream_t st);
+int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
+                                uint32_t *driving, cudaStream_t st);
+int launch_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out, cudaStream_t st);
 
 // helpers
 int launch_fleet_init(int32_t *zone, int64_t C, int64_t cars_per_zone, int64_t car_offset, cudaStream_t st);

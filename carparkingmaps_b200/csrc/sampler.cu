@@ -25,12 +25,12 @@ __global__ void __launch_bounds__(kStepThreads) k_step_gather(const StepArgs a)
 {
     const int64_t N = a.N, C = a.C;
     const double *__restrict__ pd = a.p_drive + N * a.hour;
-    const double *__restrict__ cdf_t = a.cdf + a.hour * N * N;
+    const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
     const uint8_t *__restrict__ rz = a.rowzero + a.hour * N;
     const int64_t NN = N * N;
     const bool inj = a.rng.mode == 1;
     const int64_t uoff = a.rng.ld * a.step;
-    double tsum = 0.0;
+    unsigned long long t_hi = 0ull, t_lo = 0ull;
     unsigned lost = 0;
 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) {
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_gather(const StepArgs a)
                 if (a.driving) atomicAdd(a.driving + (z - 1), 1u);                // saveresults.jl:13-15
                 if (inj) u2 = a.rng.u_dest[i + uoff];
                 if (!rz[z - 1]) {                                                 // resampling.jl:35-36
-                    const double *__restrict__ row = cdf_t + (int64_t)(z - 1) * N;
+                    const double *__restrict__ row = cdf_t + (int64_t)(z - 1) * a.ldc;
                     dest = cdf_search([&](int32_t k) { return __ldg(row + k); }, (int32_t)N, u2);   // :38-45
                 }
                 if (a.with_time) {                                                // resampling.jl:53-78
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_gather(const StepArgs a)
                         dd = truncnormal(mean, 0.1 * mean, u4);                   // :73-74
                         wrote_time = true;
                     }
-                    tsum += tt;
+                    fx_add(t_hi, t_lo, tt);
                 }
             }
             a.zone[i] = dest;                                                     // :81-83
@@ -83,16 +83,18 @@ __global__ void __launch_bounds__(kStepThreads) k_step_gather(const StepArgs a)
         }
     }
 
-    // deterministic per-block driving-time partial (each block owns one slot across steps)
-    __shared__ double s_part[kStepThreads / 32];
+    // fixed-point driving-time total: integer block reduction, then two global atomics per CTA
     if (a.with_time) {
-        tsum = warp_sum(tsum);
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = tsum;
+        __shared__ unsigned long long red[2];
+        if (threadIdx.x < 2) red[threadIdx.x] = 0ull;
+        __syncthreads();
+        t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo);
+        if ((threadIdx.x & 31) == 0) { if (t_hi) atomicAdd(&red[0], t_hi); if (t_lo) atomicAdd(&red[1], t_lo); }
         __syncthreads();
         if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int w = 0; w < kStepThreads / 32; ++w) s += s_part[w];
-            a.time_partials[blockIdx.x] += s;
+            const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
+            if (hi) atomicAdd(a.t_hi, hi);
+            if (lo32) atomicAdd(a.t_lo, lo32);
         }
     }
     if (lost) atomicAdd(a.lost, (unsigned long long)lost);

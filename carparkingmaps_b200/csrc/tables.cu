@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(64) k_pdest_norm(const double *__restrict__ p_
 // ------------------------------------------------------------------------------------------------
 template <bool DIVIDE>
 __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, const double *__restrict__ norm, int64_t N,
-                                                   int64_t T, double *__restrict__ cdf, uint8_t *__restrict__ rowzero)
+                                                   int64_t T, double *__restrict__ cdf, int64_t ldc, uint8_t *__restrict__ rowzero)
 {
     __shared__ double tile[4][32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
     bool div = false;
     if (DIVIDE) { nf = norm[ic + N * t]; div = nf > 0.0; }   // NaN -> skip (:40)
     double run = 0.0;
-    double *out = cdf + (t * N + i0) * N;
+    double *out = cdf + (t * N + i0) * ldc;
     const int64_t rows = (N - i0 < 32) ? (N - i0) : 32;
     for (int64_t j0 = 0; j0 < N; j0 += 32) {
         double v[32];
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
         }
         __syncwarp();
         if (j0 + lane < N)
-            for (int64_t r = 0; r < rows; ++r) out[r * N + j0 + lane] = tile[w][lane][r];
+            for (int64_t r = 0; r < rows; ++r) out[r * ldc + j0 + lane] = tile[w][lane][r];
         __syncwarp();
     }
     if (live) rowzero[t * N + i] = (run == 0.0) ? 1 : 0;               // sum(distribution) == 0 (:35)
@@ -215,18 +215,18 @@ int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double
     return 2;
 }
 
-int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, uint8_t *rowzero, cudaStream_t st)
+int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, uint8_t *rowzero, cudaStream_t st)
 {
     dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
-    k_cdf_build<false><<<g, 128, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, rowzero);
+    k_cdf_build<false><<<g, 128, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, ldc, rowzero);
     return 1;
 }
 
-int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, uint8_t *rowzero,
-                         cudaStream_t st)
+int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc,
+                         uint8_t *rowzero, cudaStream_t st)
 {
     dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
-    k_cdf_build<true><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, rowzero);
+    k_cdf_build<true><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, rowzero);
     return 1;
 }
 

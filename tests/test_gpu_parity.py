@@ -295,3 +295,98 @@ def test_philox_vs_stream_monte_carlo_chi_square(ctx):
         pvals.append(stats.chi2.sf(chi2, keep.sum() - 1))
     assert min(pvals) > 1e-4 and np.median(pvals) > 0.05, pvals
     city.close(); fleet.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bucket sampler (cars grouped by zone, CDF rows staged in shared memory) == gather sampler == oracle
+# ---------------------------------------------------------------------------------------------------------
+from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_GATHER  # noqa: E402
+
+
+def _dev(u):
+    """numpy [C,S] (Fortran) -> device pointer with the same column-major layout (engine API takes device pointers)"""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(u.T)).cuda()
+    return t, t.data_ptr()
+
+
+@pytest.mark.parametrize("N,cpz,density,skew", [(5, 900, 1.0, False), (33, 100, 0.5, False), (100, 300, 1.0, True),
+                                                 (257, 40, 0.09, False), (64, 200, 1.0, True)])
+@pytest.mark.parametrize("mode", ["philox", "injected"])
+def test_bucket_sampler_bit_exact(ctx, N, cpz, density, skew, mode):
+    C = N * cpz
+    dm, dist = synth_city(N, T, seed=N, density=density)
+    pd, px = _tables(dm, dist, N)
+    city = City(ctx, N, T).upload(dm, dist).set_pdrive(pd).set_pdest(px)
+    zone0 = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
+    if skew:   # most cars start in one zone: a bucket far larger than one work item (2,048 cars)
+        zone0[: C * 3 // 4] = 2
+    fb, fg = Fleet(ctx, C), Fleet(ctx, C)
+    zone_o = zone0.copy()
+    keep = []
+    for stream, n_steps, with_time in [(0, T - 1, False), (1, T, True)]:
+        if mode == "philox":
+            r_o = O.Rng(mode="philox", seed=9, stream=stream)
+            rb = rg = Rng(mode="philox", seed=9, stream=stream)
+        else:
+            rs = np.random.default_rng(100 + stream)
+            us = [np.asfortranarray(rs.random((C, n_steps))) for _ in range(4)]
+            us[0][::97, :] = 0.05; us[1][::89, 3] = 0.0          # forced drivers, a few u = 0 sentinels -> lost cars
+            r_o = O.Rng(mode="injected", u_drive=us[0], u_dest=us[1], u_time=us[2], u_dist=us[3])
+            dev = [_dev(u) for u in us]; keep.append(dev)
+            rb = rg = Rng(mode="injected", u_drive=dev[0][1], u_dest=dev[1][1], u_time=dev[2][1], u_dist=dev[3][1])
+        if stream == 0:
+            fb.set_zones(zone0); fg.set_zones(zone0)
+        fb.run_day(city, n_steps, with_time=with_time, rng=rb, sampler=SAMPLER_BUCKET)
+        fg.run_day(city, n_steps, with_time=with_time, rng=rg, sampler=SAMPLER_GATHER)
+        pk0, dr0, ts0, lost0 = O.day_counts(zone_o, N, T, n_steps, 1, pd, px, dm, dist, r_o, with_time)
+        for f in (fb, fg):
+            pk, dr, ts, lost = f.counts()
+            np.testing.assert_array_equal(pk, pk0)
+            np.testing.assert_array_equal(dr, dr0)
+            assert lost == lost0
+            np.testing.assert_allclose(ts, ts0, rtol=TIME_RTOL)
+            np.testing.assert_array_equal(f.zones(), zone_o)
+        assert fb.counts()[2] == fg.counts()[2]                  # fixed-point time sum: identical across samplers
+        if mode == "injected" and stream == 0:
+            assert lost0 > 0
+    city.close(); fb.close(); fg.close()
+
+
+def test_bucket_sampler_nan_rows_and_lost_bin(ctx):
+    """edge-case city: NaN rows (cars get lost), all-zero rows (cars stay), NaN p_drive rows (never drive)"""
+    dm, dist = edge_case_city(T)
+    N, cpz = 6, 700
+    C = N * cpz
+    pd, px = _tables(dm, dist, N)
+    city = City(ctx, N, T).upload(dm, dist).set_pdrive(pd).set_pdest(px)
+    # p_drive rows 2 and 4 are zero there; force some driving everywhere to reach the NaN row of zone 3
+    pd2 = np.asfortranarray(np.where(pd == 0, 0.3, pd)); city.set_pdrive(pd2)
+    zone_o = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
+    f = Fleet(ctx, C).set_zones(zone_o)
+    f.run_day(city, T, with_time=True, rng=Rng(seed=4, stream=1), sampler=SAMPLER_BUCKET)
+    pk0, dr0, ts0, lost0 = O.day_counts(zone_o, N, T, T, 1, pd2, px, dm, dist, O.Rng(mode="philox", seed=4, stream=1), True)
+    pk, dr, ts, lost = f.counts()
+    assert lost0 > 0 and lost == lost0
+    np.testing.assert_array_equal(pk, pk0)
+    np.testing.assert_array_equal(dr, dr0)
+    np.testing.assert_allclose(ts, ts0, rtol=TIME_RTOL)
+    np.testing.assert_array_equal(f.zones(), zone_o)
+    city.close(); f.close()
+
+
+def test_bucket_sampler_per_minute_steps_and_odd_sizes(ctx):
+    N, cpz, sph = 37, 111, 3      # odd N: CDF rows are padded to 16 doubles for the TMA bulk copy
+    C = N * cpz
+    dm, dist = synth_city(N, T, seed=13, density=1.0)
+    pd, px = _tables(dm, dist, N)
+    city = City(ctx, N, T).upload(dm, dist).set_pdrive(pd).set_pdest(px)
+    zone_o = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
+    f = Fleet(ctx, C).init(cpz)
+    f.run_day(city, T * sph, with_time=True, steps_per_hour=sph, rng=Rng(seed=6, stream=2), sampler=SAMPLER_BUCKET)
+    pk0, dr0, ts0, _ = O.day_counts(zone_o, N, T, T * sph, sph, pd, px, dm, dist, O.Rng(mode="philox", seed=6, stream=2), True)
+    pk, dr, ts, _ = f.counts()
+    np.testing.assert_array_equal(pk, pk0)
+    np.testing.assert_array_equal(dr, dr0)
+    np.testing.assert_allclose(ts, ts0, rtol=TIME_RTOL)
+    city.close(); f.close()
