@@ -39,76 +39,80 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// try_wait suspends in hardware for a bounded time per call; the spin bound turns a lost TMA completion
+// (which would otherwise hang the GPU) into a trap the host sees as a launch failure.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
 }
 
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout of k_bucket_sample
 // ------------------------------------------------------------------------------------------------
 struct SampleSmem {
-    double *row[2];
-    uint32_t *hist;
-    int32_t *dest_s;
-    uint16_t *rank_s;
-    uint16_t *srch_idx;
-    double *srch_u;
+    double *row;          // [ldc]   the origin's CDF row (TMA destination)
+    double *srch_u;       // [CH]    u_dest of the compacted drivers
+    uint32_t *hist;       // [N+1]   per-item destination counts, then bucket bases
+    uint16_t *dest_s;     // [CH]    destination bin per car of the item
+    uint16_t *rank_s;     // [CH]    rank among the item's cars with the same destination
+    uint16_t *srch_idx;   // [CH]    slot of each compacted driver
+    uint16_t *touched;    // [CH+2]  destination bins with a non-zero count (so per-item work is O(cars), not O(N))
     uint64_t *bar;
-    uint32_t *misc;   // [0] n_search, [1] n_drive
+    uint32_t *misc;       // [0] n_search, [1] n_drive, [2] n_touched
 };
 
-__host__ __device__ inline size_t sample_smem_bytes(int64_t N, int64_t ldc, int CH, int nbuf)
+__host__ __device__ inline size_t hist_bytes(int64_t N) { return ((size_t)(N + 1) * 4 + 15) / 16 * 16; }
+__host__ __device__ inline size_t sample_smem_bytes(int64_t N, int64_t ldc, int CH)
 {
-    size_t b = (size_t)nbuf * ldc * 8;          // rows (16-byte aligned by construction)
-    b += (size_t)CH * 8;                        // srch_u
-    b += ((size_t)(N + 1) * 4 + 15) / 16 * 16;  // hist
-    b += (size_t)CH * 4;                        // dest_s
-    b += (size_t)CH * 2 * 2;                    // rank_s, srch_idx
-    b += 64;                                    // barriers + misc
-    return b;
+    return (size_t)ldc * 8 + (size_t)CH * 8 + hist_bytes(N) + (size_t)CH * 2 * 3 + (size_t)(CH + 8) * 2 + 64;
 }
 
-__device__ __forceinline__ SampleSmem carve(unsigned char *base, int64_t N, int64_t ldc, int CH, int nbuf)
+__device__ __forceinline__ SampleSmem carve(unsigned char *p, int64_t N, int64_t ldc, int CH)
 {
     SampleSmem s;
-    unsigned char *p = base;
-    s.row[0] = reinterpret_cast<double *>(p);
-    s.row[1] = reinterpret_cast<double *>(p + (nbuf > 1 ? (size_t)ldc * 8 : 0));
-    p += (size_t)nbuf * ldc * 8;
+    s.row = reinterpret_cast<double *>(p); p += (size_t)ldc * 8;
     s.srch_u = reinterpret_cast<double *>(p); p += (size_t)CH * 8;
-    s.hist = reinterpret_cast<uint32_t *>(p); p += ((size_t)(N + 1) * 4 + 15) / 16 * 16;
-    s.dest_s = reinterpret_cast<int32_t *>(p); p += (size_t)CH * 4;
+    s.hist = reinterpret_cast<uint32_t *>(p); p += hist_bytes(N);
+    s.dest_s = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
     s.rank_s = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
     s.srch_idx = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
+    s.touched = reinterpret_cast<uint16_t *>(p); p += (size_t)(CH + 8) * 2;
     s.bar = reinterpret_cast<uint64_t *>(p); p += 16;
     s.misc = reinterpret_cast<uint32_t *>(p);
     return s;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_bucket_sample
+// k_bucket_sample.  One work item = up to CH cars of one zone.  Several small CTAs per SM run items in
+// different phases, which is what hides the three latencies on an item's critical path (car-id load, CDF-row
+// TMA, the global atomics that reserve ranges in the destination buckets).
 // ------------------------------------------------------------------------------------------------
-template <int NBUF>
-__global__ void __launch_bounds__(kBucketThreads, 2) k_bucket_sample(const BucketArgs a)
+template <int THREADS, int CH>
+__global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int THREADS = kBucketThreads, CH = kBucketChunk, R = CH / THREADS;
+    constexpr int R = CH / THREADS;
     const int64_t N = a.N, NN = a.N * a.N;
+    const int Ni = (int)N;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    SampleSmem s = carve(smem_raw, N, a.ldc, CH, NBUF);
-    const uint32_t row_bytes = (uint32_t)(((N * 8 + 15) / 16) * 16);
+    SampleSmem s = carve(smem_raw, N, a.ldc, CH);
+    const uint32_t row_bytes = (uint32_t)(a.ldc * 8);   // CDF row + its guide table in one bulk copy
     const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
     const double *__restrict__ pd_t = a.p_drive + N * a.hour;
     const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
@@ -116,115 +120,126 @@ __global__ void __launch_bounds__(kBucketThreads, 2) k_bucket_sample(const Bucke
     const int64_t uoff = a.rng.ld * a.step;
     const int n_items = *a.n_items;
 
-    if (tid == 0) {
-        mbar_init(&s.bar[0], 1);
-        mbar_init(&s.bar[1], 1);
-        fence_mbar_init();
-    }
+    if (tid == 0) { mbar_init(&s.bar[0], 1); fence_mbar_init(); }
+    for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(s.hist)[x] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 4) s.misc[tid] = 0u;
     __syncthreads();
 
-    uint32_t parity[2] = {0u, 0u};
-    int buf = 0;
-    int w = blockIdx.x;
-    if (w < n_items && tid == 0) {
-        const int4 it = __ldg(a.items + w);
-        if (it.x < N) {
-            mbar_expect_tx(&s.bar[0], row_bytes);
-            tma_bulk_g2s(s.row[0], cdf_t + (int64_t)it.x * a.ldc, row_bytes, &s.bar[0]);
-        }
-    }
+    uint32_t par = 0u;
     unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
 
-    for (; w < n_items; w += gridDim.x) {
+    uint32_t *const hist = s.hist;
+    uint16_t *const touched = s.touched;
+    uint32_t *const n_touched = &s.misc[2];
+    int prev_nt = 0;   // #bins the previous item touched (every thread keeps its own copy: no extra barrier)
+
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int4 it = __ldg(a.items + w);   // x = bin (0..N-1 zone, N = lost), y = first slot, z = #cars
         const int bin = it.x, lo = it.y, n = it.z;
-        const bool is_zone = bin < N;
-        // prefetch the next item's row into the other buffer (single-buffer variant: issued after phase B)
-        if (NBUF == 2 && tid == 0) {
-            const int wn = w + gridDim.x;
-            if (wn < n_items) {
-                const int4 nx = __ldg(a.items + wn);
-                if (nx.x < N) {
-                    fence_proxy_async();
-                    mbar_expect_tx(&s.bar[buf ^ 1], row_bytes);
-                    tma_bulk_g2s(s.row[buf ^ 1], cdf_t + (int64_t)nx.x * a.ldc, row_bytes, &s.bar[buf ^ 1]);
+        const bool is_zone = bin < Ni;
+        if (is_zone && tid == 0) {   // the row buffer was last read before the previous item's phase-B barrier
+            fence_proxy_async();
+            mbar_expect_tx(&s.bar[0], row_bytes);
+            tma_bulk_g2s(s.row, cdf_t + (int64_t)bin * a.ldc, row_bytes, &s.bar[0]);
+        }
+        const int32_t *__restrict__ perm = a.perm_cur + lo;
+
+        // car ids of all rounds first, so their load latencies overlap each other and the clean-up below
+        int32_t ids[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) { const int k = r * THREADS + tid; ids[r] = (is_zone && k < n) ? __ldg(perm + k) : 0; }
+        // clear the histogram bins the previous item touched (O(cars), not O(N))
+        for (int i = tid; i < prev_nt; i += THREADS) hist[touched[i]] = 0u;
+        __syncthreads();
+
+        if (!is_zone) {
+            // lost cars (zone 0) are carried along: never drive, never counted in a zone
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int k = r * THREADS + tid;
+                if (k < n) { s.dest_s[k] = (uint16_t)bin; s.rank_s[k] = (uint16_t)k; }
+            }
+            if (tid == 0) { hist[bin] = (uint32_t)n; touched[0] = (uint16_t)bin; *n_touched = 1u; lost += (unsigned long long)n; }
+            __syncthreads();
+        } else {
+            const double pd = __ldg(pd_t + bin);
+            const bool rowzero = rz_t[bin] != 0;
+            unsigned nd_warp = 0;
+            // ---- phase A: Bernoulli drive decision for every car of the item (src/resampling.jl:11-22) ----
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r * THREADS >= n) break;          // block-uniform: the ballots below stay convergent
+                const int k = r * THREADS + tid;
+                const bool active = k < n;
+                bool drive = false;
+                double u2 = 0.0;
+                if (active) {
+                    const int64_t id = ids[r];
+                    double u1;
+                    if (inj) u1 = a.rng.u_drive[id + uoff];
+                    else philox_pair(a.rng, id, (uint32_t)a.step, 0u, u1, u2);
+                    drive = u1 <= pd;                                   // :15 (<=; NaN p_drive parks)
+                    if (drive && inj && !rowzero) u2 = a.rng.u_dest[id + uoff];
+                }
+                const bool search = drive && !rowzero;
+                const bool stay = active && !search;                    // parked, or all-zero row (:35-36)
+                const uint32_t m_drive = __ballot_sync(0xffffffffu, drive);
+                const uint32_t m_stay = __ballot_sync(0xffffffffu, stay);
+                const uint32_t m_s = m_drive & ~m_stay;                 // == ballot(search)
+                nd_warp += __popc(m_drive);
+                // stayers: rank inside the own-zone bin via one warp-aggregated shared atomic;
+                // searchers: compact (slot, u_dest) so that phase B runs without idle lanes
+                uint32_t base = 0, off = 0;
+                if (lane == 0) {
+                    if (m_stay) {
+                        base = atomicAdd(&hist[bin], (uint32_t)__popc(m_stay));
+                        if (base == 0u) touched[atomicAdd(n_touched, 1u)] = (uint16_t)bin;
+                    }
+                    if (m_s) off = atomicAdd(&s.misc[0], (uint32_t)__popc(m_s));
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (stay) { s.dest_s[k] = (uint16_t)bin; s.rank_s[k] = (uint16_t)(base + __popc(m_stay & lt_mask)); }
+                if (search) {
+                    const uint32_t q = off + __popc(m_s & lt_mask);
+                    s.srch_idx[q] = (uint16_t)k;
+                    s.srch_u[q] = u2;
                 }
             }
-        }
-        for (int x = tid; x <= N; x += THREADS) s.hist[x] = 0u;
-        if (tid == 0) { s.misc[0] = 0u; s.misc[1] = 0u; }
-        __syncthreads();
+            if (rowzero && a.with_time && lane == 0) t_hi += 300ull * nd_warp;   // origin == destination: 5 min (:58-59)
+            if (lane == 0 && nd_warp) atomicAdd(&s.misc[1], nd_warp);
+            __syncthreads();
 
-        const double pd = is_zone ? __ldg(pd_t + bin) : -1.0;
-        const bool rowzero = is_zone ? (rz_t[bin] != 0) : true;
-        unsigned n_drive_thread = 0;
-
-        // ---- phase A: Bernoulli drive decision for every car of the item (src/resampling.jl:11-22) ----
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = r * THREADS + tid;
-            const bool active = k < n;
-            bool drive = false;
-            double u2 = 0.0;
-            if (active && is_zone) {
-                const int64_t id = a.perm_cur[lo + k];
-                double u1;
-                if (inj) u1 = a.rng.u_drive[id + uoff];
-                else philox_pair(a.rng, id, (uint32_t)a.step, 0u, u1, u2);
-                drive = u1 <= pd;                                   // :15 (<=; NaN p_drive parks)
-                if (drive && inj && !rowzero) u2 = a.rng.u_dest[id + uoff];
+            // ---- phase B: categorical destination from the staged CDF row (src/resampling.jl:26-49) ----
+            const int n_search = (int)s.misc[0];
+            if (n_search > 0 || true) {   // every thread observes the TMA completion (phase parity stays in step)
+                mbar_wait(&s.bar[0], par & 1u);
+                par ^= 1u;
             }
-            n_drive_thread += drive ? 1u : 0u;
-            const bool search = drive && !rowzero;
-            const bool stay = active && !search;                    // parked, all-zero row (:35-36), or lost
-            if (a.with_time && drive && rowzero) t_hi += 300ull;    // origin == destination: 5 minutes (:58-59)
-            // stayers: rank inside the own-zone bin via one warp-aggregated shared atomic
-            const uint32_t m_stay = __ballot_sync(0xffffffffu, stay);
-            uint32_t base = 0;
-            if (m_stay && lane == (__ffs(m_stay) - 1)) base = atomicAdd(&s.hist[bin], (uint32_t)__popc(m_stay));
-            base = __shfl_sync(0xffffffffu, base, m_stay ? (__ffs(m_stay) - 1) : 0);
-            if (stay) { s.dest_s[k] = bin; s.rank_s[k] = (uint16_t)(base + __popc(m_stay & lt_mask)); }
-            // searchers: compact (slot, u_dest) so that phase B runs without idle lanes
-            const uint32_t m_s = __ballot_sync(0xffffffffu, search);
-            uint32_t off = 0;
-            if (m_s && lane == (__ffs(m_s) - 1)) off = atomicAdd(&s.misc[0], (uint32_t)__popc(m_s));
-            off = __shfl_sync(0xffffffffu, off, m_s ? (__ffs(m_s) - 1) : 0);
-            if (search) {
-                const uint32_t q = off + __popc(m_s & lt_mask);
-                s.srch_idx[q] = (uint16_t)k;
-                s.srch_u[q] = u2;
-            }
-        }
-        {
-            unsigned nd = n_drive_thread;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) nd += __shfl_xor_sync(0xffffffffu, nd, o);
-            if (lane == 0 && nd) atomicAdd(&s.misc[1], nd);
-        }
-        if (!is_zone) lost += (tid == 0) ? (unsigned long long)n : 0ull;
-        __syncthreads();
-
-        // ---- phase B: categorical destination from the staged CDF row (src/resampling.jl:26-49) ----
-        const int n_search = (int)s.misc[0];
-        if (is_zone) {
-            mbar_wait(&s.bar[buf], parity[buf]);
-            parity[buf] ^= 1u;
-            const double *row = s.row[buf];
+            const double *row = s.row;
+            const uint16_t *gd = reinterpret_cast<const uint16_t *>(s.row + a.goff);
             for (int q = tid; q < n_search; q += THREADS) {
                 const int k = s.srch_idx[q];
                 const double u2 = s.srch_u[q];
-                const int32_t d = cdf_search([&](int32_t j) { return row[j]; }, (int32_t)N, u2);   // 1-based, 0 = none
-                const int dbin = d ? d - 1 : (int)N;
-                s.dest_s[k] = dbin;
-                s.rank_s[k] = (uint16_t)atomicAdd(&s.hist[dbin], 1u);
+                // guided lower_bound on the staged row; acceptance test as in src/resampling.jl:40 (u = 0, u above the
+                // last entry or a NaN sum -> sentinel 0 = lost)
+                const int32_t d = cdf_search_guided([&](int32_t j) { return row[j]; }, [&](int32_t bb) { return (int32_t)gd[bb]; },
+                                                    Ni, a.G, u2);
+                const bool hit = d > 0;
+                const int pos = d - 1;
+                const int dbin = hit ? pos : Ni;
+                const uint32_t old = atomicAdd(&hist[dbin], 1u);
+                if (old == 0u) touched[atomicAdd(n_touched, 1u)] = (uint16_t)dbin;
+                s.dest_s[k] = (uint16_t)dbin;
+                s.rank_s[k] = (uint16_t)old;
                 if (a.with_time) {                                   // src/resampling.jl:53-70 (time only: counts mode)
                     if (dbin == bin) t_hi += 300ull;
-                    else if (d >= 1) {
-                        const int64_t id = a.perm_cur[lo + k];
+                    else if (hit) {
+                        const int64_t id = __ldg(perm + k);
                         double u3, u4;
                         if (inj) u3 = a.rng.u_time[id + uoff];
                         else philox_pair(a.rng, id, (uint32_t)a.step, 1u, u3, u4);
-                        const int64_t od = (int64_t)bin + N * (int64_t)(d - 1);
+                        const int64_t od = (int64_t)bin + N * (int64_t)dbin;
                         const double mean = __ldg(a.dm + od + NN * a.hour);
                         double sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
                         if (sd == 0.0) sd = 0.1 * mean;
@@ -232,40 +247,33 @@ __global__ void __launch_bounds__(kBucketThreads, 2) k_bucket_sample(const Bucke
                     }
                 }
             }
-        }
-        __syncthreads();
-        if (NBUF == 1 && tid == 0) {   // single buffer: the row is free again, fetch the next item's row now
-            const int wn = w + gridDim.x;
-            if (wn < n_items) {
-                const int4 nx = __ldg(a.items + wn);
-                if (nx.x < N) {
-                    fence_proxy_async();
-                    mbar_expect_tx(&s.bar[0], row_bytes);
-                    tma_bulk_g2s(s.row[0], cdf_t + (int64_t)nx.x * a.ldc, row_bytes, &s.bar[0]);
-                }
-            }
+            __syncthreads();
         }
 
-        // ---- phase C: reserve a range in every destination bucket (one global atomic per item x destination) ----
-        for (int x = tid; x <= N; x += THREADS) {
-            const uint32_t c = s.hist[x];
-            if (c) s.hist[x] = atomicAdd(a.cnt_next + x, c);
+        // ---- phase C: reserve a range in every touched destination bucket (one global atomic per item x destination) ----
+        {
+            const int nt = (int)*n_touched;
+            prev_nt = nt;
+            for (int i = tid; i < nt; i += THREADS) {
+                const int b = touched[i];
+                hist[b] = atomicAdd(a.cnt_next + b, hist[b]);
+            }
+            if (tid == 0 && is_zone && s.misc[1]) atomicAdd(a.drv + bin, s.misc[1]);   // src/saveresults.jl:13-15
         }
-        if (tid == 0 && is_zone && s.misc[1]) atomicAdd(a.drv + bin, s.misc[1]);   // src/saveresults.jl:13-15
         __syncthreads();
 
         // ---- phase D: destination bin and position inside it, per slot (coalesced) ----
+        if (tid == 0) { s.misc[0] = 0u; s.misc[1] = 0u; *n_touched = 0u; }   // all were consumed before the barrier above
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int k = r * THREADS + tid;
             if (k < n) {
                 const int db = s.dest_s[k];
-                a.dest[lo + k] = db;
-                a.pos[lo + k] = s.hist[db] + s.rank_s[k];
+                a.dest[lo + k] = (uint16_t)db;
+                a.pos[lo + k] = hist[db] + s.rank_s[k];
             }
         }
         __syncthreads();
-        if (NBUF == 2) buf ^= 1;
     }
 
     // driving-time and lost-car totals: integer block reduction, two global atomics per CTA
@@ -326,23 +334,24 @@ __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot 
 
 // start[] (shared, NB+1 entries incl. total) must already hold the exclusive scan of cnt[]
 __device__ void write_items(const uint32_t *__restrict__ cnt, const uint32_t *start, uint32_t *itoff, uint32_t *warp_tot,
-                            int NB, int4 *__restrict__ items, int32_t *__restrict__ n_items)
+                            int NB, uint32_t chunk, int4 *__restrict__ items, int32_t *__restrict__ n_items)
 {
-    for (int x = threadIdx.x; x < NB; x += blockDim.x) itoff[x] = (cnt[x] + kBucketChunk - 1) / kBucketChunk;
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) itoff[x] = (cnt[x] + chunk - 1) / chunk;
     __syncthreads();
     const uint32_t total = block_exclusive_scan(itoff, NB, warp_tot);
     for (int x = threadIdx.x; x < NB; x += blockDim.x) {
         const uint32_t c = cnt[x];
         uint32_t o = itoff[x];
-        for (uint32_t j = 0; j * kBucketChunk < c; ++j)
-            items[o + j] = make_int4(x, (int)(start[x] + j * kBucketChunk), (int)min((uint32_t)kBucketChunk, c - j * kBucketChunk), 0);
+        for (uint32_t j = 0; j * chunk < c; ++j)
+            items[o + j] = make_int4(x, (int)(start[x] + j * chunk), (int)min(chunk, c - j * chunk), 0);
     }
     if (threadIdx.x == 0) *n_items = (int32_t)total;
 }
 
 // day start / stand-alone: start[] and the item list from cnt[]
-__global__ void __launch_bounds__(1024) k_bucket_items(const uint32_t *__restrict__ cnt, int NB, uint32_t *__restrict__ start_out,
-                                                       int4 *__restrict__ items, int32_t *__restrict__ n_items)
+__global__ void __launch_bounds__(1024) k_bucket_items(const uint32_t *__restrict__ cnt, int NB, uint32_t chunk,
+                                                       uint32_t *__restrict__ start_out, int4 *__restrict__ items,
+                                                       int32_t *__restrict__ n_items)
 {
     extern __shared__ uint32_t sm[];   // start[NB] | itoff[NB] | warp_tot[33]
     uint32_t *start = sm, *itoff = sm + NB, *warp_tot = sm + 2 * NB;
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(1024) k_bucket_items(const uint32_t *__restric
     __syncthreads();
     block_exclusive_scan(start, NB, warp_tot);
     if (start_out) for (int x = threadIdx.x; x < NB; x += blockDim.x) start_out[x] = start[x];
-    write_items(cnt, start, itoff, warp_tot, NB, items, n_items);
+    write_items(cnt, start, itoff, warp_tot, NB, chunk, items, n_items);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -372,7 +381,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scatter(const ScatterArgs a)
     }
     if (blockIdx.x == 0 && a.items) {
         __syncthreads();
-        write_items(a.cnt_next, start, itoff, warp_tot, NB, a.items, a.n_items);
+        write_items(a.cnt_next, start, itoff, warp_tot, NB, (uint32_t)a.chunk, a.items, a.n_items);
     }
 }
 
@@ -436,64 +445,84 @@ __global__ void k_finalize_time(const unsigned long long *hi, const unsigned lon
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-bool bucket_supported(int64_t N, int64_t ldc, int *nbuf_out, size_t *smem_out)
+// Two shapes: small CTAs (256 threads, items of 1,024 cars) so that four fit on an SM when the CDF row is small
+// (N up to ~3,000), otherwise 512 threads / 2,048 cars with as many CTAs as shared memory allows.
+static int bucket_shape(int64_t N, int64_t ldc, size_t *smem_out, int *ctas_out)
 {
-    if (N + 1 > 65535) return false;
-    for (int nbuf = 2; nbuf >= 1; --nbuf) {
-        const size_t b = sample_smem_bytes(N, ldc, kBucketChunk, nbuf);
-        // two CTAs per SM need 2*b <= 227 KB; a single CTA may use up to 227 KB
-        if ((nbuf == 2 && b <= 113 * 1024) || (nbuf == 1 && b <= 227 * 1024) || (nbuf == 2 && b <= 227 * 1024 && false)) {
-            if (nbuf_out) *nbuf_out = nbuf;
-            if (smem_out) *smem_out = b;
-            return true;
-        }
+    const size_t small = sample_smem_bytes(N, ldc, 1024), big = sample_smem_bytes(N, ldc, 2048);
+    const size_t sm_total = 227 * 1024;
+    if (4 * (small + 1024) <= sm_total) { *smem_out = small; *ctas_out = (int)(sm_total / (small + 1024)); return 1; }
+    if (big + 1024 <= sm_total) { *smem_out = big; *ctas_out = (int)(sm_total / (big + 1024)); return 2; }
+    return 0;
+}
+
+int bucket_chunk(int64_t N, int64_t ldc)
+{
+    size_t smem; int ctas;
+    const int shape = bucket_shape(N, ldc, &smem, &ctas);
+    return shape == 1 ? 1024 : shape == 2 ? 2048 : 0;
+}
+
+bool bucket_supported(int64_t N, int64_t ldc)
+{
+    return N + 1 <= 65535 && bucket_chunk(N, ldc) != 0;
+}
+
+// opt in to > 48 KB of dynamic shared memory, raising the per-kernel limit only when a launch needs more
+template <typename K>
+static void ensure_smem(K kernel, size_t bytes, size_t &granted)
+{
+    if (bytes > granted) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        granted = bytes;
     }
-    return false;
 }
 
 int launch_bucket_sample(const BucketArgs &a, cudaStream_t st)
 {
-    int nbuf = 0; size_t smem = 0;
-    if (!bucket_supported(a.N, a.ldc, &nbuf, &smem)) return -1;
-    static bool attr_set[3] = {false, false, false};
-    if (nbuf == 2) {
-        if (!attr_set[2]) { cudaFuncSetAttribute(k_bucket_sample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[2] = true; }
-        k_bucket_sample<2><<<kSMs * 2, kBucketThreads, smem, st>>>(a);
-    } else {
-        if (!attr_set[1]) { cudaFuncSetAttribute(k_bucket_sample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_set[1] = true; }
-        k_bucket_sample<1><<<kSMs * (smem <= 113 * 1024 ? 2 : 1), kBucketThreads, smem, st>>>(a);
-    }
+    size_t smem = 0; int ctas = 0;
+    const int shape = bucket_shape(a.N, a.ldc, &smem, &ctas);
+    static size_t granted[3] = {0, 0, 0};
+    if (shape == 1) {
+        if (ctas > 8) ctas = 8;
+        ensure_smem(k_bucket_sample<256, 1024>, smem, granted[1]);
+        k_bucket_sample<256, 1024><<<kSMs * ctas, 256, smem, st>>>(a);
+    } else if (shape == 2) {
+        if (ctas > 4) ctas = 4;
+        ensure_smem(k_bucket_sample<512, 2048>, smem, granted[2]);
+        k_bucket_sample<512, 2048><<<kSMs * ctas, 512, smem, st>>>(a);
+    } else return -1;
     return 1;
 }
 
 static size_t scan_smem(int NB) { return ((size_t)2 * NB + 40) * sizeof(uint32_t); }
 
-int launch_bucket_items(const uint32_t *cnt, int NB, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st)
+int launch_bucket_items(const uint32_t *cnt, int NB, int chunk, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_bucket_items, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-    k_bucket_items<<<1, 1024, scan_smem(NB), st>>>(cnt, NB, start_out, items, n_items);
+    static size_t granted = 48 * 1024;
+    ensure_smem(k_bucket_items, scan_smem(NB), granted);
+    k_bucket_items<<<1, 1024, scan_smem(NB), st>>>(cnt, NB, (uint32_t)chunk, start_out, items, n_items);
     return 1;
 }
 
 int launch_bucket_scatter(const ScatterArgs &a, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_bucket_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    static size_t granted = 48 * 1024;
+    ensure_smem(k_bucket_scatter, scan_smem(a.NB), granted);
     int64_t blocks = (a.C + 1023) / 1024;
     if (blocks > kSMs * 2) blocks = kSMs * 2;
     k_bucket_scatter<<<(unsigned)blocks, 1024, scan_smem(a.NB), st>>>(a);
     return 1;
 }
 
-int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
+int launch_bucketize(const int32_t *zone, int64_t C, int NB, int chunk, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
                      int32_t *perm, int4 *items, int32_t *n_items, cudaStream_t st)
 {
     cudaMemsetAsync(cnt0, 0, (size_t)NB * sizeof(uint32_t), st);
     cudaMemsetAsync(cursor_tmp, 0, (size_t)NB * sizeof(uint32_t), st);
     const int g = sampler_grid(C);
     k_bucket_hist<<<g, 256, 0, st>>>(zone, C, NB, cnt0);
-    launch_bucket_items(cnt0, NB, start_tmp, items, n_items, st);
+    launch_bucket_items(cnt0, NB, chunk, start_tmp, items, n_items, st);
     k_bucket_place<<<g, 256, 0, st>>>(zone, C, NB, start_tmp, cursor_tmp, perm);
     return 3;
 }

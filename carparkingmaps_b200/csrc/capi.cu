@@ -86,7 +86,10 @@ struct cpm_city {
     cpm_ctx *ctx = nullptr;
     int64_t N = 0, T = 0;
     DevBuf dm, dist, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
-    int64_t ldc = 0;   // CDF row stride in doubles: N rounded up to 16 (128-byte rows: TMA-aligned for any N)
+    // CDF row block: N doubles, padded to goff doubles, then the row's guide table (G+1 uint16, padded): ldc doubles
+    // in total, a multiple of 16 bytes so that a row block is one TMA bulk copy for any N
+    int64_t ldc = 0;
+    int32_t goff = 0, G = 0;
     bool have_inputs = false, have_meansum = false, have_pdrive = false, have_cdf = false, have_pdest = false;
 };
 
@@ -317,7 +320,15 @@ static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, 
 }
 static int32_t city_alloc_cdf(cpm_city *c)
 {
-    c->ldc = (c->N + 15) / 16 * 16;
+    c->goff = (int32_t)((c->N + 1) / 2 * 2);                      // 16-byte aligned guide
+    c->G = 0;
+    if (c->N + 1 <= 65535) {                                       // guide entries are uint16
+        int64_t g = 64;
+        while (g < (c->N + 3) / 4 && g < 8192) g *= 2;             // ~4 CDF entries per guide cell
+        c->G = (int32_t)g;
+    }
+    const int64_t guide_doubles = c->G ? ((int64_t)c->G + 1 + 7) / 8 * 2 : 0;   // (G+1) uint16 rounded up to 16 bytes
+    c->ldc = c->goff + guide_doubles;
     TRY(c->cdf.ensure((size_t)c->N * c->ldc * c->T * sizeof(double)));
     TRY(c->rowzero.ensure((size_t)c->N * c->T));
     return CPM_OK;
@@ -331,7 +342,7 @@ static int32_t city_build_pdestin_async(cpm_city *c, double e_dest)
     TRY(city_alloc_cdf(c));
     LAUNCH(c->ctx, launch_pdestin(c->dm.as<double>(), c->N, c->T, e_dest, c->p_dest.as<double>(), c->norm.as<double>(), c->ctx->st));
     LAUNCH(c->ctx, launch_cdf_normalise(c->p_dest.as<double>(), c->norm.as<double>(), c->N, c->T, c->cdf.as<double>(),
-                                        c->ldc, c->rowzero.as<uint8_t>(), c->ctx->st));
+                                        c->ldc, c->goff, c->G, c->rowzero.as<uint8_t>(), c->ctx->st));
     c->have_cdf = true;
     c->have_pdest = true;
     return CPM_OK;
@@ -374,7 +385,7 @@ extern "C" int32_t cpm_city_set_pdest(cpm_city *c, const double *p_dest)
     TRY(c->p_dest.ensure(NN * c->T * sizeof(double)));
     TRY(city_alloc_cdf(c));
     CU(cudaMemcpyAsync(c->p_dest.p, p_dest, NN * c->T * sizeof(double), cudaMemcpyHostToDevice, c->ctx->st));
-    LAUNCH(c->ctx, launch_cdf_from_pdest(c->p_dest.as<double>(), c->N, c->T, c->cdf.as<double>(), c->ldc, c->rowzero.as<uint8_t>(), c->ctx->st));
+    LAUNCH(c->ctx, launch_cdf_from_pdest(c->p_dest.as<double>(), c->N, c->T, c->cdf.as<double>(), c->ldc, c->goff, c->G, c->rowzero.as<uint8_t>(), c->ctx->st));
     CU(cudaStreamSynchronize(c->ctx->st));
     c->have_cdf = true;
     c->have_pdest = true;
@@ -530,7 +541,7 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
     memset(&a, 0, sizeof a);
     a.p_drive = city->p_drive.as<double>();
     a.cdf = city->cdf.as<double>();
-    a.ldc = city->ldc;
+    a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
     a.rowzero = city->rowzero.as<uint8_t>();
     a.dm = city->dm.as<double>();
     a.dist = city->dist.as<double>();
@@ -563,7 +574,8 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     const int64_t N = city->N, C = f->C;
     const int NB = (int)N + 1;
     const int64_t S = o->n_steps;
-    const size_t max_items = (size_t)NB + (size_t)(C / kBucketChunk) + 2;
+    const int chunk = bucket_chunk(N, city->ldc);
+    const size_t max_items = (size_t)NB + (size_t)(C / chunk) + 2;
     TRY(f->perm[0].ensure((size_t)C * 4)); TRY(f->perm[1].ensure((size_t)C * 4));
     TRY(f->dest.ensure((size_t)C * 4)); TRY(f->pos.ensure((size_t)C * 4));
     TRY(f->bcnt.ensure((size_t)(S + 1) * NB * 4)); TRY(f->bdrv.ensure((size_t)S * NB * 4));
@@ -578,23 +590,23 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     } else {
         if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
         f->cur = 0;
-        LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), C, NB, bcnt, f->start_tmp.as<uint32_t>(), f->cursor_tmp.as<uint32_t>(),
+        LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), C, NB, chunk, bcnt, f->start_tmp.as<uint32_t>(), f->cursor_tmp.as<uint32_t>(),
                                      f->perm[0].as<int32_t>(), f->items.as<int4>(), f->n_items.as<int32_t>(), ctx->st));
     }
     Scalars *sc = f->scalars.as<Scalars>();
     BucketArgs a;
     memset(&a, 0, sizeof a);
-    a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc;
+    a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
     a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
     a.N = N; a.T_tab = city->T; a.C = C;
-    a.dest = f->dest.as<int32_t>(); a.pos = f->pos.as<uint32_t>();
+    a.dest = f->dest.as<uint16_t>(); a.pos = f->pos.as<uint32_t>();
     a.with_time = o->with_time;
     a.rng = make_rng(o->rng, C);
     a.items = f->items.as<int4>(); a.n_items = f->n_items.as<int32_t>();
     a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo; a.lost = &sc->lost;
     ScatterArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.NB = NB; sa.dest = a.dest; sa.pos = a.pos; sa.C = C;
+    sa.NB = NB; sa.dest = a.dest; sa.pos = a.pos; sa.C = C; sa.chunk = chunk;
     sa.items = f->items.as<int4>(); sa.n_items = f->n_items.as<int32_t>();
     TRY(profile_open(ctx, S));
     for (int64_t s = 0; s < S; ++s) {
@@ -631,7 +643,7 @@ static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o
         if (o->with_time) ARG(o->rng.u_time && (traj == nullptr || o->rng.u_dist));
     }
     const int64_t N = city->N;
-    const bool can_bucket = traj == nullptr && bucket_supported(N, city->ldc, nullptr, nullptr);
+    const bool can_bucket = traj == nullptr && city->G > 0 && bucket_supported(N, city->ldc);
     if (o->sampler == CPM_SAMPLER_BUCKET && !can_bucket)
         return fail(CPM_ERR_ARG, "the bucket sampler needs N + 1 <= 65535, a CDF row that fits shared memory, and no trajectory recording");
     const bool use_bucket = can_bucket && o->sampler != CPM_SAMPLER_GATHER;
@@ -972,14 +984,15 @@ extern "C" int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const 
     const size_t CT = (size_t)C * T, NT = (size_t)N * T;
     TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
     TRY(ctx->tmp.ensure(CT * sizeof(double)));
-    TRY(ctx->partials.ensure(2 * NT * sizeof(uint32_t) + (2 * NT + T) * sizeof(double)));
+    TRY(ctx->partials.ensure(2 * NT * sizeof(uint32_t) + (2 * NT + 2 * T) * sizeof(double)));
     uint32_t *cnt = ctx->partials.as<uint32_t>();
     double *outp = reinterpret_cast<double *>(cnt + 2 * NT);   // NT even multiples keep 8-byte alignment
     CU(cudaMemcpyAsync(ctx->traj_state.p, state, CT * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(ctx->tmp.p, trans, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 1: drive flag
     CU(cudaMemsetAsync(cnt, 0, 2 * NT * sizeof(uint32_t), ctx->st));
     LAUNCH(ctx, launch_traj_histogram(ctx->traj_state.as<int64_t>(), ctx->tmp.as<double>(), C, N, T, cnt, cnt + NT, ctx->st));
-    LAUNCH(ctx, launch_normalise_counts(cnt, cnt + NT, N, T, C, outp, outp + NT, outp + 2 * NT, nullptr, ctx->st));
+    LAUNCH(ctx, launch_normalise_counts(cnt, cnt + NT, N, T, C, outp, outp + NT, outp + 2 * NT,
+                                        reinterpret_cast<unsigned long long *>(outp + 2 * NT + T), ctx->st));
     if (parking) CU(cudaMemcpyAsync(parking, outp, NT * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     if (driving) CU(cudaMemcpyAsync(driving, outp + NT, NT * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     if (traffic) CU(cudaMemcpyAsync(traffic, outp + 2 * NT, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));

@@ -120,6 +120,24 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+// The same draw with a guide ("cut-point") table: guide[b] = #{j : cdf[j] < b/G}, b = 0..G, G a power of two.
+// For b = floor(u*G):  guide[b] <= lower_bound(u) <= guide[b+1], so the binary search runs over a handful of
+// entries instead of N.  All comparisons are the exact fp64 ones of cdf_search, hence the same index.
+template <typename LoadF, typename LoadG>
+__device__ __forceinline__ int32_t cdf_search_guided(LoadF load, LoadG guide, int32_t n, int32_t G, double u)
+{
+    if (!(u > 0.0)) return 0;
+    int32_t lo, hi;
+    if (u < 1.0) { const int32_t b = (int32_t)(u * (double)G); lo = guide(b); hi = guide(b + 1); }
+    else { lo = guide(G); hi = n; }
+    while (lo < hi) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (load(mid) < u) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= n) return 0;
+    return (u <= load(lo)) ? lo + 1 : 0;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

@@ -19,19 +19,20 @@ int launch_pdrive_finish(const double *mean_sum, int64_t N, int64_t T, double p_
 int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double *p_dest, double *norm,
                    cudaStream_t st);
 // cdf[T][N][N] (destination fastest) + rowzero[T][N] from p_dest[N,N,T]: left-to-right fp64 running sum
-int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, uint8_t *rowzero,
-                          cudaStream_t st);
+int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff, int G,
+                          uint8_t *rowzero, cudaStream_t st);
 
 // fused: p_dest /= norm (where norm > 0) and the CDF build in one pass (src/createpdestin.jl:38-46)
-int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc,
-                         uint8_t *rowzero, cudaStream_t st);
+int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff,
+                         int G, uint8_t *rowzero, cudaStream_t st);
 
 // ---- sampler.cu -------------------------------------------------------------------------------
 struct StepArgs {
     // tables
     const double *p_drive;   // [N,T]
-    const double *cdf;       // [T][N][ldc] destination fastest, rows padded to ldc (multiple of 16) doubles
-    int64_t ldc;
+    const double *cdf;       // [T][N] row blocks of ldc doubles: N CDF entries (destination fastest), padding to
+    int64_t ldc;             //        goff doubles, then the row's guide table (G+1 uint16); ldc*8 is a multiple of 16
+    int32_t goff, G;         // guide offset inside a row block (in doubles) and guide resolution (0 = no guide)
     const uint8_t *rowzero;  // [T][N]
     const double *dm;        // [N,N,T,2] (with_time only)
     const double *dist;      // [N,N]     (with_time only)
@@ -61,13 +62,11 @@ int launch_step_gather(const StepArgs &a, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int n, double *out, cudaStream_t st);
 
 // ---- bucket.cu --------------------------------------------------------------------------------
-constexpr int kBucketThreads = 512;
-constexpr int kBucketChunk = 2048;   // cars per work item (one zone, or a chunk of a large zone)
 struct BucketArgs {
-    const double *p_drive; const double *cdf; int64_t ldc; const uint8_t *rowzero; const double *dm;
+    const double *p_drive; const double *cdf; int64_t ldc; int32_t goff, G; const uint8_t *rowzero; const double *dm;
     int64_t N, T_tab;
     const int32_t *perm_cur;   // [C] car ids grouped by zone bin
-    int32_t *dest;             // [C] destination bin per slot (N = lost)
+    uint16_t *dest;            // [C] destination bin per slot (N = lost)
     uint32_t *pos;             // [C] position inside the destination bucket
     int64_t C, step, hour;
     int32_t with_time;
@@ -80,15 +79,17 @@ struct BucketArgs {
 };
 struct ScatterArgs {
     const uint32_t *cnt_next; int NB;
-    const int32_t *dest; const uint32_t *pos; const int32_t *perm_cur; int32_t *perm_next; int64_t C;
+    const uint16_t *dest; const uint32_t *pos; const int32_t *perm_cur; int32_t *perm_next; int64_t C;
     int32_t *zone_out;         // nullable: car-id indexed zone (written on the last step of a day)
     int4 *items; int32_t *n_items;   // next step's work items (written by block 0)
+    int chunk;                 // cars per work item
 };
-bool bucket_supported(int64_t N, int64_t ldc, int *nbuf_out, size_t *smem_out);
+bool bucket_supported(int64_t N, int64_t ldc);
+int bucket_chunk(int64_t N, int64_t ldc);   // cars per work item for this table size (0 = unsupported)
 int launch_bucket_sample(const BucketArgs &a, cudaStream_t st);
 int launch_bucket_scatter(const ScatterArgs &a, cudaStream_t st);
-int launch_bucket_items(const uint32_t *cnt, int NB, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st);
-int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
+int launch_bucket_items(const uint32_t *cnt, int NB, int chunk, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st);
+int launch_bucketize(const int32_t *zone, int64_t C, int NB, int chunk, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
                      int32_t *perm, int4 *items, int32_t *n_items, cudaStream_t st);
 int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
                                 uint32_t *driving, cudaStream_t st);

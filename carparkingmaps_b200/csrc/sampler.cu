@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(kStepThreads) k_step_gather(const StepArgs a)
                 if (inj) u2 = a.rng.u_dest[i + uoff];
                 if (!rz[z - 1]) {                                                 // resampling.jl:35-36
                     const double *__restrict__ row = cdf_t + (int64_t)(z - 1) * a.ldc;
-                    dest = cdf_search([&](int32_t k) { return __ldg(row + k); }, (int32_t)N, u2);   // :38-45
+                    if (a.G > 0) {
+                        const uint16_t *__restrict__ gd = reinterpret_cast<const uint16_t *>(row + a.goff);
+                        dest = cdf_search_guided([&](int32_t k) { return __ldg(row + k); },
+                                                 [&](int32_t b) { return (int32_t)__ldg(gd + b); }, (int32_t)N, a.G, u2);   // :38-45
+                    } else dest = cdf_search([&](int32_t k) { return __ldg(row + k); }, (int32_t)N, u2);
                 }
                 if (a.with_time) {                                                // resampling.jl:53-78
                     if (dest == z) { tt = 300.0; dd = 1.0; wrote_time = true; }   // :58-60
@@ -219,37 +223,48 @@ int launch_sum_f64(const double *x, int64_t n, double *partials, int n_partials,
     return 2;
 }
 
-// parking = counts / C (saveresults.jl:20); traffic = minmax over hours of column sums (saveresults.jl:23-28)
-__global__ void k_normalise_counts(const uint32_t *__restrict__ parking, const uint32_t *__restrict__ driving, int64_t N,
-                                   int64_t T, int64_t C, double *__restrict__ parking_out, double *__restrict__ driving_out,
-                                   double *__restrict__ traffic_out, unsigned long long *__restrict__ traffic_counts_out)
+// parking = counts / C (saveresults.jl:20); traffic = minmax over hours of column sums (saveresults.jl:23-28).
+// One block per hour: coalesced pass over the hour's column; then one tiny block for the min-max over hours.
+__global__ void __launch_bounds__(256) k_normalise_cols(const uint32_t *__restrict__ parking, const uint32_t *__restrict__ driving,
+                                                        int64_t N, int64_t C, double *__restrict__ parking_out,
+                                                        double *__restrict__ driving_out, unsigned long long *__restrict__ col_sum)
 {
-    extern __shared__ unsigned long long s_col[];   // [T]
-    for (int64_t t = threadIdx.x; t < T; t += blockDim.x) s_col[t] = 0ull;
-    __syncthreads();
-    for (int64_t k = threadIdx.x; k < N * T; k += blockDim.x) {
+    const int64_t t = blockIdx.x;
+    unsigned long long s = 0ull;
+    for (int64_t z = threadIdx.x; z < N; z += blockDim.x) {
+        const int64_t k = z + N * t;
         if (parking_out) parking_out[k] = (double)parking[k] / (double)C;
         const uint32_t d = driving[k];
         if (driving_out) driving_out[k] = (double)d;
-        if (d) atomicAdd(&s_col[k / N], (unsigned long long)d);
+        s += d;
     }
+    __shared__ unsigned long long sp[8];
+    s = warp_sum_u64(s);
+    if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned long long mn = s_col[0], mx = s_col[0];
-        for (int64_t t = 0; t < T; ++t) { if (s_col[t] < mn) mn = s_col[t]; if (s_col[t] > mx) mx = s_col[t]; }
-        for (int64_t t = 0; t < T; ++t) {
-            if (traffic_counts_out) traffic_counts_out[t] = s_col[t];
-            if (traffic_out) traffic_out[t] = ((double)s_col[t] - (double)mn) / ((double)mx - (double)mn);
-        }
+        unsigned long long r = 0ull;
+        for (int w = 0; w < 8; ++w) r += sp[w];
+        col_sum[t] = r;
     }
 }
+__global__ void k_normalise_traffic(const unsigned long long *__restrict__ col_sum, int64_t T, double *__restrict__ traffic_out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        unsigned long long mn = col_sum[0], mx = col_sum[0];
+        for (int64_t t = 0; t < T; ++t) { if (col_sum[t] < mn) mn = col_sum[t]; if (col_sum[t] > mx) mx = col_sum[t]; }
+        for (int64_t t = 0; t < T; ++t) traffic_out[t] = ((double)col_sum[t] - (double)mn) / ((double)mx - (double)mn);
+    }
+}
+// traffic_counts_out [T] is required (it doubles as the column-sum scratch)
 int launch_normalise_counts(const uint32_t *parking, const uint32_t *driving, int64_t N, int64_t T, int64_t C,
                             double *parking_out, double *driving_out, double *traffic_out,
                             unsigned long long *traffic_counts_out, cudaStream_t st)
 {
-    k_normalise_counts<<<1, 1024, (size_t)T * sizeof(unsigned long long), st>>>(parking, driving, N, T, C, parking_out,
-                                                                             driving_out, traffic_out, traffic_counts_out);
-    return 1;
+    k_normalise_cols<<<(unsigned)T, 256, 0, st>>>(parking, driving, N, C, parking_out, driving_out, traffic_counts_out);
+    if (!traffic_out) return 1;
+    k_normalise_traffic<<<1, 32, 0, st>>>(traffic_counts_out, T, traffic_out);
+    return 2;
 }
 
 }  // namespace cpm

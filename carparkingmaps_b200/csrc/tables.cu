@@ -205,6 +205,50 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
     if (live) rowzero[t * N + i] = (run == 0.0) ? 1 : 0;               // sum(distribution) == 0 (:35)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Guide ("cut-point") table of every CDF row: guide[b] = #{j : cdf[j] < b/G}, b = 0..G (common.cuh:
+// cdf_search_guided).  One warp per row; entry j owns the thresholds b/G in (cdf[j-1], cdf[j]] (exact: G is a power
+// of two), thresholds above the last finite sum see every finite entry.  A NaN sum (and everything after it) owns none.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_guide_build(double *__restrict__ cdf, int64_t ldc, int goff, int G, int64_t N, int64_t rows)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const double *rowp = cdf + row * ldc;
+    uint16_t *g = reinterpret_cast<uint16_t *>(cdf + row * ldc + goff);
+    const double Gd = (double)G;
+    double carry = 0.0;
+    int64_t n_valid = N;
+    for (int64_t jb = 0; jb < N; jb += 32) {
+        const int64_t j = jb + lane;
+        const bool valid = j < N;
+        const double cur = valid ? rowp[j] : carry;
+        double prev = __shfl_up_sync(0xffffffffu, cur, 1);
+        if (lane == 0) prev = carry;
+        carry = __shfl_sync(0xffffffffu, cur, 31);
+        if (valid && cur > prev) {
+            const double lo_d = prev * Gd, hi_d = cur * Gd;
+            const int b_lo = (lo_d >= Gd) ? G + 1 : (int)floor(lo_d) + 1;
+            const int b_hi = (hi_d >= Gd) ? G : (int)floor(hi_d);
+            for (int b = b_lo; b <= b_hi; ++b) g[b] = (uint16_t)j;
+        }
+        const uint32_t nanmask = __ballot_sync(0xffffffffu, valid && cur != cur);
+        if (nanmask && n_valid == N) n_valid = jb + __ffs(nanmask) - 1;
+    }
+    const double last = n_valid > 0 ? rowp[n_valid - 1] : 0.0;
+    const double lo_d = last * Gd;
+    const int b_lo = (lo_d >= Gd) ? G + 1 : (int)floor(lo_d) + 1;
+    for (int b = b_lo + lane; b <= G; b += 32) g[b] = (uint16_t)n_valid;
+    if (lane == 0) g[0] = 0;
+}
+
+static void launch_guide(double *cdf, int64_t ldc, int goff, int G, int64_t N, int64_t T, cudaStream_t st)
+{
+    const int64_t rows = N * T;
+    k_guide_build<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cdf, ldc, goff, G, N, rows);
+}
+
 int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double *p_dest, double *norm, cudaStream_t st)
 {
     const int64_t NN = N * N;
@@ -215,19 +259,22 @@ int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double
     return 2;
 }
 
-int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, uint8_t *rowzero, cudaStream_t st)
+int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff, int G,
+                          uint8_t *rowzero, cudaStream_t st)
 {
     dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
     k_cdf_build<false><<<g, 128, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, ldc, rowzero);
-    return 1;
+    if (G > 0) launch_guide(cdf, ldc, goff, G, N, T, st);
+    return G > 0 ? 2 : 1;
 }
 
-int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc,
-                         uint8_t *rowzero, cudaStream_t st)
+int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff,
+                         int G, uint8_t *rowzero, cudaStream_t st)
 {
     dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
     k_cdf_build<true><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, rowzero);
-    return 1;
+    if (G > 0) launch_guide(cdf, ldc, goff, G, N, T, st);
+    return G > 0 ? 2 : 1;
 }
 
 }  // namespace cpm
