@@ -750,7 +750,7 @@ extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cp
 }
 
 extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params, int64_t P,
-                             uint64_t seed, int32_t common_random_numbers, int64_t *traffic_counts, double *A_drive,
+                             uint64_t seed, const uint32_t *streams, int64_t *traffic_counts, double *A_drive,
                              double *parking)
 {
     ARG(city && initial_zones && params && P >= 1 && C >= 1);
@@ -776,7 +776,7 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
         memset(&o, 0, sizeof o);
         o.n_steps = T; o.steps_per_hour = 1; o.with_time = 1; o.sampler = CPM_SAMPLER_AUTO;
         o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
-        o.rng.stream = common_random_numbers ? 1u : (uint32_t)(2 + p);
+        o.rng.stream = streams ? streams[p] : (uint32_t)(2 + p);
         if (rc == CPM_OK) rc = run_day_async(city, work, &o, nullptr);
         if (rc == CPM_OK) rc = normalise_async(work, N, T, C);
         if (rc != CPM_OK) break;

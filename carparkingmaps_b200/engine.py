@@ -227,8 +227,9 @@ def sample_dataset(city: City, fleet: Fleet, *, e_drive=0.5, e_dest=2, p_min=0.1
     return parking, traffic, A.value, lost.value
 
 
-def sweep(city: City, initial_zones, params, *, seed=0, common_random_numbers=False, want_parking=False):
+def sweep(city: City, initial_zones, params, *, seed=0, common_random_numbers=False, want_parking=False, streams=None):
     """Model-selection sweep over P parameter sets (rows of `params`: e_drive, e_dest, p_min, p_max).
+    `streams`: Philox stream id per set (default 2 + p; all equal with common_random_numbers).
     Returns (traffic_counts int64[T,P], A_drive[P], parking[N,T,P] or None)."""
     params = np.asarray(params, dtype=np.float64).reshape(-1, 4)
     P = params.shape[0]
@@ -237,6 +238,9 @@ def sweep(city: City, initial_zones, params, *, seed=0, common_random_numbers=Fa
     tc = np.empty((city.T, P), dtype=np.int64, order="F")
     A = np.empty(P)
     parking = np.empty((city.N, city.T, P), order="F") if want_parking else None
-    L.check(L.lib().cpm_sweep(city._h, _ptr(z), z.shape[0], arr, P, int(seed), int(common_random_numbers),
-                              _ptr(tc), _ptr(A), _ptr(parking)))
+    if streams is None and common_random_numbers:
+        streams = np.ones(P, dtype=np.uint32)
+    st = None if streams is None else np.ascontiguousarray(streams, dtype=np.uint32)
+    assert st is None or st.shape == (P,)
+    L.check(L.lib().cpm_sweep(city._h, _ptr(z), z.shape[0], arr, P, int(seed), _ptr(st), _ptr(tc), _ptr(A), _ptr(parking)))
     return tc, A, parking

@@ -1,0 +1,183 @@
+# CarParkingMapsGPU.jl -- drop-in replacement of the reference's hot-path functions, backed by libcpm.so.
+#
+# Usage (in the reference's main.jl, replacing the seven `include("src/....jl")` lines of main.jl:13-19):
+#
+#     ENV["LIBCPM"] = "/path/to/carparkingmaps_b200/libcpm.so"
+#     include("CarParkingMapsGPU.jl")        # defines createpdrive, createpdestin, initializestates,
+#                                            # solveinitialvalueproblem, resampling, averagedrivingtime, correctparameters
+#
+# Same names, same positional signatures, same in-place mutation and return values as
+# src/createpdrive.jl:3, src/createpdestin.jl:3, src/initializestates.jl:4, src/solveinitialvalueproblem.jl:4,
+# src/resampling.jl:3, src/averagedrivingtime.jl:3, src/correctparameters.jl:3.  Like the originals, the functions
+# read the globals T, p_min, p_max, e_drive, e_dest, cars_per_zone from Main at call time (main.jl:37-42) and pass
+# them by value across the C ABI (include/cpm.h).  There is no CUDA.jl kernel code generation and no CPU fallback:
+# every call is a `ccall` into hand-written sm_100a kernels, and a non-zero status becomes a Julia `error`.
+#
+# This file cannot be executed in the build environment (no Julia toolchain in the image); it mirrors, call for
+# call, the ctypes binding in carparkingmaps_b200/api.py that the GPU parity tests exercise.
+
+module CarParkingMapsGPU
+
+export createpdrive, createpdestin, initializestates, solveinitialvalueproblem, resampling,
+       averagedrivingtime, correctparameters, zonehistogram, sampledataset, cpm_seed!
+
+const LIBCPM = get(ENV, "LIBCPM", joinpath(@__DIR__, "..", "libcpm.so"))
+
+# struct cpm_rng (include/cpm.h)
+struct CpmRng
+    mode::Int32
+    stream::UInt32
+    seed::UInt64
+    car_offset::Int64
+    u_drive::Ptr{Float64}
+    u_dest::Ptr{Float64}
+    u_time::Ptr{Float64}
+    u_dist::Ptr{Float64}
+end
+
+struct CpmParams
+    e_drive::Float64
+    e_dest::Float64
+    p_min::Float64
+    p_max::Float64
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+const SEED = Ref{UInt64}(0)           # the reference never seeds Julia's RNG; Philox needs an explicit key
+const STREAM = Ref{UInt32}(0)
+
+cpm_seed!(s::Integer) = (SEED[] = UInt64(s); STREAM[] = 0; nothing)
+
+function check(rc::Int32)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:cpm_last_error, LIBCPM), Cstring, ()))
+    error("libcpm error $rc: $msg")
+end
+
+function ctx()
+    if CTX[] == C_NULL
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:cpm_ctx_create, LIBCPM), Int32, (Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), 0, C_NULL, out))
+        CTX[] = out[]
+        atexit(() -> ccall((:cpm_ctx_destroy, LIBCPM), Int32, (Ptr{Cvoid},), CTX[]))
+    end
+    return CTX[]
+end
+
+nextrng() = (STREAM[] += 1; CpmRng(0, STREAM[], SEED[], 0, C_NULL, C_NULL, C_NULL, C_NULL))
+
+g(name::Symbol) = getfield(Main, name)     # the reference's untyped globals (main.jl:37-42)
+
+# src/createpdrive.jl:3-38
+function createpdrive(datamatrix::Array{Float64,4}, distance_matrix_km::Array{Float64,2}, number_zones)
+    N, T = Int64(number_zones), Int64(g(:T))
+    p_drive = Array{Float64}(undef, N, T)
+    check(ccall((:cpm_create_pdrive, LIBCPM), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Float64, Float64, Float64, Ptr{Float64}),
+                ctx(), datamatrix, distance_matrix_km, N, T, Float64(g(:p_min)), Float64(g(:p_max)), Float64(g(:e_drive)), p_drive))
+    return p_drive
+end
+
+# src/createpdestin.jl:3-50
+function createpdestin(datamatrix::Array{Float64,4}, number_zones)
+    N, T = Int64(number_zones), Int64(g(:T))
+    p_dest = Array{Float64}(undef, N, N, T)
+    check(ccall((:cpm_create_pdestin, LIBCPM), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Float64, Ptr{Float64}),
+                ctx(), datamatrix, N, T, Float64(g(:e_dest)), p_dest))
+    return p_dest
+end
+
+# src/initializestates.jl:4-22
+function initializestates(C)
+    C, T = Int64(C), Int64(g(:T))
+    state_matrix = Array{Int64}(undef, C, T)
+    transition_matrix = Array{Float64}(undef, C, T, 4)
+    check(ccall((:cpm_initialize_states, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Float64}),
+                ctx(), C, T, Int64(g(:cars_per_zone)), state_matrix, transition_matrix))
+    return state_matrix, transition_matrix
+end
+
+# src/solveinitialvalueproblem.jl:4-62 (mutates state_matrix / transition_matrix, returns initial_state)
+function solveinitialvalueproblem(state_matrix::Array{Int64,2}, transition_matrix::Array{Float64,3}, p_drive, p_dest, C, number_zones;
+                                  rng::CpmRng = nextrng())
+    C, N, T = Int64(C), Int64(number_zones), Int64(g(:T))
+    initial_state = Vector{Int64}(undef, C)
+    lost = Ref{Int64}(0)
+    check(ccall((:cpm_solve_ivp, LIBCPM), Int32,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Ref{CpmRng}, Ptr{Int64}, Ref{Int64}),
+                ctx(), state_matrix, transition_matrix, p_drive, p_dest, C, N, T, Ref(rng), initial_state, lost))
+    for t = 1:(T-1)
+        println(trunc(Int, t / 0.23), "% of the Initial Value Problem is solved")      # :54
+    end
+    lost[] > 0 && @warn "cars whose destination draw found no bin (reference: BoundsError)" visits = lost[]
+    return initial_state
+end
+
+# src/resampling.jl:3-89 (mutates and returns both arrays)
+function resampling(state_matrix::Array{Int64,2}, transition_matrix::Array{Float64,3}, C, number_zones, p_drive, p_dest,
+                    datamatrix, distance_matrix_km; rng::CpmRng = nextrng())
+    C, N, T = Int64(C), Int64(number_zones), Int64(g(:T))
+    lost = Ref{Int64}(0)
+    check(ccall((:cpm_resampling, LIBCPM), Int32,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ref{CpmRng}, Ref{Int64}),
+                ctx(), state_matrix, transition_matrix, C, N, T, p_drive, p_dest, datamatrix, distance_matrix_km, Ref(rng), lost))
+    for t = 1:T
+        println(trunc(Int, t / 0.23), "% of the dataset is simulated")                  # :84
+    end
+    lost[] > 0 && @warn "cars whose destination draw found no bin (reference: BoundsError)" visits = lost[]
+    return state_matrix, transition_matrix
+end
+
+# src/averagedrivingtime.jl:3-12
+function averagedrivingtime(C, A_drive, transition_matrix::Array{Float64,3})
+    out = Ref{Float64}(0.0)
+    check(ccall((:cpm_average_driving_time, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Int64, Float64, Ptr{Float64}, Ref{Float64}),
+                ctx(), Int64(C), Int64(g(:T)), Float64(A_drive), transition_matrix, out))
+    return out[]
+end
+
+# src/correctparameters.jl:3-23
+function correctparameters(p_min_next, p_max_next, p_min, p_max)
+    out = zeros(2)
+    check(ccall((:cpm_correct_parameters, LIBCPM), Int32, (Float64, Float64, Float64, Float64, Ptr{Float64}),
+                Float64(p_min_next), Float64(p_max_next), Float64(p_min), Float64(p_max), out))
+    return out[1], out[2]
+end
+
+# the histogram / normalisation block of saveresults (src/saveresults.jl:6-28)
+function zonehistogram(number_zones, state_matrix::Array{Int64,2}, transition_matrix::Array{Float64,3}, C)
+    N, T = Int64(number_zones), Int64(g(:T))
+    parking_cars, driving_cars, traffic = zeros(N, T), zeros(N, T), zeros(1, T)
+    check(ccall((:cpm_zone_histogram, LIBCPM), Int32,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx(), state_matrix, transition_matrix, Int64(C), N, T, parking_cars, driving_cars, traffic))
+    return parking_cars, driving_cars, traffic
+end
+
+# main.jl:82-98 in ONE call, device-resident: only datamatrix / distance matrix go up and the reduced results
+# (parking densities [N,T], traffic activity [T], A_drive increment) come back.  This is the fast path; the
+# function-by-function API above moves the multi-GB state / transition matrices across PCIe on every call.
+function sampledataset(datamatrix::Array{Float64,4}, distance_matrix_km::Array{Float64,2}, number_zones; seed::Integer = SEED[])
+    N, T = Int64(number_zones), Int64(g(:T))
+    cpz = Int64(g(:cars_per_zone))
+    city, fleet = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cpm_city_create, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx(), N, T, city))
+    check(ccall((:cpm_fleet_create, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx(), N * cpz, fleet))
+    parking, traffic, A, lost = zeros(N, T), zeros(1, T), Ref{Float64}(0.0), Ref{Int64}(0)
+    try
+        check(ccall((:cpm_city_upload, LIBCPM), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), city[], datamatrix, distance_matrix_km))
+        pr = CpmParams(Float64(g(:e_drive)), Float64(g(:e_dest)), Float64(g(:p_min)), Float64(g(:p_max)))
+        check(ccall((:cpm_sample_dataset, LIBCPM), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CpmParams}, Int64, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}),
+                    city[], fleet[], Ref(pr), cpz, UInt64(seed), Int32(0), parking, traffic, A, lost))
+    finally
+        ccall((:cpm_fleet_destroy, LIBCPM), Int32, (Ptr{Cvoid},), fleet[])
+        ccall((:cpm_city_destroy, LIBCPM), Int32, (Ptr{Cvoid},), city[])
+    end
+    return parking, traffic, A[], lost[]
+end
+
+end # module
+
+using .CarParkingMapsGPU

@@ -199,10 +199,12 @@ int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cpm_params *p
 
 /* Model-selection sweep (README.md:956-1316, 1435-1681, 1831-2278 as a batched grid): for each of
  * P parameter sets, rebuild the table(s), restart from `initial_zones` and resample one day.
+ * streams (nullable, [P]): Philox stream id of each set (default 2 + p); equal ids give common random
+ * numbers, global set indices make a sharded sweep independent of the sharding.
  * Outputs (host): traffic_counts Int64 [T,P] raw driving totals per hour, A_drive [P],
  * parking (nullable) Float64 [N,T,P] densities. */
 int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params,
-                  int64_t P, uint64_t seed, int32_t common_random_numbers, int64_t *traffic_counts,
+                  int64_t P, uint64_t seed, const uint32_t *streams, int64_t *traffic_counts,
                   double *A_drive, double *parking);
 
 #ifdef __cplusplus
