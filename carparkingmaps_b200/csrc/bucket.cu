@@ -212,15 +212,15 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 
             // ---- phase B: categorical destination from the staged CDF row (src/resampling.jl:26-49) ----
             const int n_search = (int)s.misc[0];
-            if (n_search > 0 || true) {   // every thread observes the TMA completion (phase parity stays in step)
-                mbar_wait(&s.bar[0], par & 1u);
-                par ^= 1u;
-            }
+            mbar_wait(&s.bar[0], par & 1u);   // every thread observes the TMA completion (phase parity stays in step)
+            par ^= 1u;
             const double *row = s.row;
             const uint16_t *gd = reinterpret_cast<const uint16_t *>(s.row + a.goff);
-            for (int q = tid; q < n_search; q += THREADS) {
-                const int k = s.srch_idx[q];
-                const double u2 = s.srch_u[q];
+            for (int q0 = 0; q0 < n_search; q0 += THREADS) {   // block-uniform trip count (ballot below)
+                const int q = q0 + tid;
+                const bool act = q < n_search;
+                const int k = act ? s.srch_idx[q] : 0;
+                const double u2 = act ? s.srch_u[q] : 0.0;
                 // guided lower_bound on the staged row; acceptance test as in src/resampling.jl:40 (u = 0, u above the
                 // last entry or a NaN sum -> sentinel 0 = lost)
                 const int32_t d = cdf_search_guided([&](int32_t j) { return row[j]; }, [&](int32_t bb) { return (int32_t)gd[bb]; },
@@ -228,8 +228,16 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
                 const bool hit = d > 0;
                 const int pos = d - 1;
                 const int dbin = hit ? pos : Ni;
-                const uint32_t old = atomicAdd(&hist[dbin], 1u);
-                if (old == 0u) touched[atomicAdd(n_touched, 1u)] = (uint16_t)dbin;
+                const uint32_t old = act ? atomicAdd(&hist[dbin], 1u) : 1u;
+                // first toucher of a bin appends it to the touched list: one shared atomic per warp, not per lane
+                const uint32_t m_new = __ballot_sync(0xffffffffu, old == 0u);
+                if (m_new) {
+                    uint32_t tbase = 0;
+                    if (lane == 0) tbase = atomicAdd(n_touched, (uint32_t)__popc(m_new));
+                    tbase = __shfl_sync(0xffffffffu, tbase, 0);
+                    if (old == 0u) touched[tbase + __popc(m_new & lt_mask)] = (uint16_t)dbin;
+                }
+                if (!act) continue;
                 s.dest_s[k] = (uint16_t)dbin;
                 s.rank_s[k] = (uint16_t)old;
                 if (a.with_time) {                                   // src/resampling.jl:53-70 (time only: counts mode)
@@ -254,9 +262,21 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
         {
             const int nt = (int)*n_touched;
             prev_nt = nt;
-            for (int i = tid; i < nt; i += THREADS) {
-                const int b = touched[i];
-                hist[b] = atomicAdd(a.cnt_next + b, hist[b]);
+            // batches of CB atomics per thread are issued back to back so that their round trips overlap
+            constexpr int CB = 4;
+            for (int i0 = 0; i0 < nt; i0 += THREADS * CB) {
+                int b[CB];
+                uint32_t c[CB];
+#pragma unroll
+                for (int u = 0; u < CB; ++u) {
+                    const int i = i0 + u * THREADS + tid;
+                    b[u] = (i < nt) ? (int)touched[i] : -1;
+                    c[u] = (b[u] >= 0) ? hist[b[u]] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < CB; ++u) if (b[u] >= 0) c[u] = atomicAdd(a.cnt_next + b[u], c[u]);
+#pragma unroll
+                for (int u = 0; u < CB; ++u) if (b[u] >= 0) hist[b[u]] = c[u];
             }
             if (tid == 0 && is_zone && s.misc[1]) atomicAdd(a.drv + bin, s.misc[1]);   // src/saveresults.jl:13-15
         }

@@ -85,7 +85,7 @@ struct cpm_ctx {
 struct cpm_city {
     cpm_ctx *ctx = nullptr;
     int64_t N = 0, T = 0;
-    DevBuf dm, dist, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
+    DevBuf dm, dist, rdist, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
     // CDF row block: N doubles, padded to goff doubles, then the row's guide table (G+1 uint16, padded): ldc doubles
     // in total, a multiple of 16 bytes so that a row block is one TMA bulk copy for any N
     int64_t ldc = 0;
@@ -254,7 +254,7 @@ extern "C" int32_t cpm_city_destroy(cpm_city *c)
     if (!c) return CPM_OK;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->st);
-    c->dm.release(); c->dist.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
+    c->dm.release(); c->dist.release(); c->rdist.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
     c->norm.release(); c->cdf.release(); c->rowzero.release();
     delete c;
     return CPM_OK;
@@ -309,9 +309,11 @@ static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, 
     if (!c->have_inputs) return fail(CPM_ERR_STATE, "createpdrive needs the city inputs (upload or synth first)");
     const size_t NT = (size_t)c->N * c->T;
     TRY(c->mean_sum.ensure(NT * sizeof(double)));
+    TRY(c->rdist.ensure((size_t)c->N * c->N * 2 * sizeof(double)));   // (dist, 1/dist) pairs
     TRY(c->p_drive.ensure(NT * sizeof(double)));
     if (!c->have_meansum) {   // parameter-independent: cached across sweeps
-        LAUNCH(c->ctx, launch_pdrive_meansum(c->dm.as<double>(), c->dist.as<double>(), c->N, c->T, c->mean_sum.as<double>(), c->ctx->st));
+        LAUNCH(c->ctx, launch_pdrive_meansum(c->dm.as<double>(), c->dist.as<double>(), c->rdist.as<double>(), c->N, c->T,
+                                             c->mean_sum.as<double>(), c->ctx->st));
         c->have_meansum = true;
     }
     LAUNCH(c->ctx, launch_pdrive_finish(c->mean_sum.as<double>(), c->N, c->T, p_min, p_max, e_drive, c->p_drive.as<double>(), c->ctx->st));
@@ -333,7 +335,7 @@ static int32_t city_alloc_cdf(cpm_city *c)
     TRY(c->rowzero.ensure((size_t)c->N * c->T));
     return CPM_OK;
 }
-static int32_t city_build_pdestin_async(cpm_city *c, double e_dest)
+static int32_t city_build_pdestin_async(cpm_city *c, double e_dest, bool write_p = true)
 {
     if (!c->have_inputs) return fail(CPM_ERR_STATE, "createpdestin needs the city inputs (upload or synth first)");
     const size_t NN = (size_t)c->N * c->N;
@@ -342,9 +344,9 @@ static int32_t city_build_pdestin_async(cpm_city *c, double e_dest)
     TRY(city_alloc_cdf(c));
     LAUNCH(c->ctx, launch_pdestin(c->dm.as<double>(), c->N, c->T, e_dest, c->p_dest.as<double>(), c->norm.as<double>(), c->ctx->st));
     LAUNCH(c->ctx, launch_cdf_normalise(c->p_dest.as<double>(), c->norm.as<double>(), c->N, c->T, c->cdf.as<double>(),
-                                        c->ldc, c->goff, c->G, c->rowzero.as<uint8_t>(), c->ctx->st));
+                                        c->ldc, c->goff, c->G, c->rowzero.as<uint8_t>(), write_p ? 1 : 0, c->ctx->st));
     c->have_cdf = true;
-    c->have_pdest = true;
+    c->have_pdest = write_p;   // without write_p the buffer holds the unnormalised stage only
     return CPM_OK;
 }
 
@@ -358,7 +360,7 @@ extern "C" int32_t cpm_city_build_pdestin(cpm_city *c, double e_dest, int32_t ke
 {
     ARG(c != nullptr);
     TRY(use(c->ctx));
-    TRY(city_build_pdestin_async(c, e_dest));
+    TRY(city_build_pdestin_async(c, e_dest, keep_p_dest != 0));
     if (!keep_p_dest) {   // p_dest is only a stage of the CDF build; drop it when the caller does not need it
         CU(cudaStreamSynchronize(c->ctx->st));
         c->p_dest.release();
@@ -716,8 +718,9 @@ extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cp
     TRY(use(ctx));
     const int64_t N = city->N, T = city->T;
     ARG(fleet->C == N * cars_per_zone);
+    city->have_meansum = false;   // one dataset pass recomputes everything, like the reference (no cached stages)
     TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive));                 // main.jl:82
-    TRY(city_build_pdestin_async(city, pr->e_dest));                                        // main.jl:85
+    TRY(city_build_pdestin_async(city, pr->e_dest, false));                                 // main.jl:85
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->st));   // main.jl:88
     fleet->car_offset = 0;
     cpm_day_opts o;
@@ -767,7 +770,7 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
     for (int64_t p = 0; rc == CPM_OK && p < P; ++p) {
         const cpm_params &pr = params[p];
         if (!have_e_dest || pr.e_dest != cur_e_dest || !city->have_cdf) {   // CDFs are shared by sets with equal e_dest
-            rc = city_build_pdestin_async(city, pr.e_dest);
+            rc = city_build_pdestin_async(city, pr.e_dest, false);
             have_e_dest = true; cur_e_dest = pr.e_dest;
         }
         if (rc == CPM_OK) rc = city_build_pdrive_async(city, pr.p_min, pr.p_max, pr.e_drive);   // mean_sum cached

@@ -10,7 +10,7 @@ namespace cpm {
 
 // ---- tables.cu --------------------------------------------------------------------------------
 // mean_sum[N,T] (src/createpdrive.jl:10-21)
-int launch_pdrive_meansum(const double *dm, const double *dist, int64_t N, int64_t T, double *mean_sum,
+int launch_pdrive_meansum(const double *dm, const double *dist, double *rdist, int64_t N, int64_t T, double *mean_sum,
                           cudaStream_t st);
 // p_drive[N,T] from mean_sum (src/createpdrive.jl:22-34)
 int launch_pdrive_finish(const double *mean_sum, int64_t N, int64_t T, double p_min, double p_max,
@@ -24,7 +24,7 @@ int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cd
 
 // fused: p_dest /= norm (where norm > 0) and the CDF build in one pass (src/createpdestin.jl:38-46)
 int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff,
-                         int G, uint8_t *rowzero, cudaStream_t st);
+                         int G, uint8_t *rowzero, int write_p, cudaStream_t st);
 
 // ---- sampler.cu -------------------------------------------------------------------------------
 struct StepArgs {

@@ -1,40 +1,72 @@
 // tables.cu -- probability tables of the HMM: createpdrive / createpdestin and the sampling CDF.
 // Reference: src/createpdrive.jl:3-38, src/createpdestin.jl:3-50 (Julia, column-major, origin index fastest).
-// All kernels are HBM-bound elementwise / scan work in fp64; no tensor cores (nothing is a contraction).
+// All kernels are elementwise / scan work in fp64 over the N x N x T grid; no tensor cores (nothing is a
+// contraction).  fp64 division is the expensive instruction on this part (a ~25-instruction sequence on a
+// half-rate pipe), so every quotient whose divisor is shared by many elements is computed as
+// "reciprocal once + two FMAs" (div_r below), which returns the same correctly rounded quotient.
 #include "kernels.h"
 
 namespace cpm {
 
+// a / d given r = 1/d correctly rounded (Markstein): q = a*r is within an ulp or two of the quotient; the residual
+// e = a - q*d is exact in an FMA; q + e*r rounds to the correctly rounded quotient.  Valid when r is finite and
+// non-zero and nothing overflows; callers check that once per divisor (or once per row) and otherwise take the
+// division instruction, so special values behave exactly like Julia's `/`.
+__device__ __forceinline__ double div_r(double a, double d, double r)
+{
+    const double q = a * r;
+    return __fma_rn(__fma_rn(-q, d, a), r, q);
+}
+__device__ __forceinline__ bool recip_ok(double r) { return fabs(r) < 1.0e300 && fabs(r) > 1.0e-300; }   // NaN -> false
+
 // ------------------------------------------------------------------------------------------------
 // createpdrive, part 1: mean_sum[i,t] = (sum_{j: m!=0} m[i,j,t]/dist[i,j]) / count   (:10-21)
-// One thread per (i,t), i fastest -> every load of the j loop is coalesced across the warp.  The
-// running sum is accumulated in ascending j exactly like the reference, so mean_sum is bit-identical
-// to a sequential fp64 evaluation (fp64 add/div are IEEE on the device).
+// One thread per (i,t), i fastest -> every load of the j loop is coalesced across the warp.  The running sum is
+// accumulated in ascending j exactly like the reference, so mean_sum is bit-identical to a sequential fp64
+// evaluation.  rdist = 1/dist is computed once per (i,j) by k_rdist instead of 24 times.
 // ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rdist(const double *__restrict__ dist, int64_t n, double2 *__restrict__ rdist)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { const double d = dist[k]; rdist[k] = make_double2(d, 1.0 / d); }
+}
+
 constexpr int kMsUnroll = 8;
 
-__global__ void __launch_bounds__(64) k_pdrive_meansum(const double *__restrict__ dm, const double *__restrict__ dist,
+__global__ void __launch_bounds__(64) k_pdrive_meansum(const double *__restrict__ dm, const double2 *__restrict__ rdist,
                                                        int64_t N, int64_t T, double *__restrict__ mean_sum)
 {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N * T) return;
-    const int64_t i = idx % N, t = idx / N;
+    // blocks of the same origin chunk and consecutive hours are adjacent in launch order, so the (dist, 1/dist) pairs
+    // they share are fetched from HBM once and then hit L2
+    const int64_t t = blockIdx.x % T;
+    const int64_t i = (int64_t)(blockIdx.x / T) * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t idx = i + N * t;
     const double *m = dm + i + N * N * t;
-    const double *d = dist + i;
+    const double2 *dr = rdist + i;
     double s = 0.0;
-    int64_t cnt = 0;
+    int cnt = 0;
     int64_t j = 0;
     for (; j + kMsUnroll <= N; j += kMsUnroll) {
-        double mv[kMsUnroll], dv[kMsUnroll];
+        double mv[kMsUnroll];
+        double2 dv[kMsUnroll];
 #pragma unroll
-        for (int u = 0; u < kMsUnroll; ++u) { mv[u] = __ldg(m + N * (j + u)); dv[u] = __ldg(d + N * (j + u)); }
+        for (int u = 0; u < kMsUnroll; ++u) { mv[u] = __ldg(m + N * (j + u)); dv[u] = __ldg(dr + N * (j + u)); }
 #pragma unroll
         for (int u = 0; u < kMsUnroll; ++u)
-            if (mv[u] != 0.0) { s = s + mv[u] / dv[u]; ++cnt; }
+            if (mv[u] != 0.0) { s = s + div_r(mv[u], dv[u].x, dv[u].y); ++cnt; }   // :15-17
     }
     for (; j < N; ++j) {
-        const double mv = __ldg(m + N * j), dv = __ldg(d + N * j);
-        if (mv != 0.0) { s = s + mv / dv; ++cnt; }
+        const double mv = __ldg(m + N * j);
+        const double2 dv = __ldg(dr + N * j);
+        if (mv != 0.0) { s = s + div_r(mv, dv.x, dv.y); ++cnt; }
+    }
+    if (!(fabs(s) < 1.0e300)) {   // a zero / non-finite distance or an overflow: redo the row with the division instruction
+        s = 0.0;
+        for (j = 0; j < N; ++j) {
+            const double mv = __ldg(m + N * j);
+            if (mv != 0.0) s = s + mv / __ldg(dr + N * j).x;
+        }
     }
     mean_sum[idx] = s / (double)cnt;   // 0/0 -> NaN, as in Julia (:20)
 }
@@ -46,14 +78,14 @@ __global__ void k_pdrive_finish(const double *__restrict__ mean_sum, int64_t N, 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     double mx = mean_sum[i], mn = mx;
-    bool nan = false;
+    bool has_nan = false;
     for (int64_t t = 0; t < T; ++t) {
         const double v = mean_sum[i + N * t];
-        nan |= isnan(v);
+        has_nan |= isnan(v);
         if (v > mx) mx = v;
         if (v < mn) mn = v;
     }
-    if (nan) mx = mn = __longlong_as_double(0x7ff8000000000000LL);
+    if (has_nan) mx = mn = __longlong_as_double(0x7ff8000000000000LL);
     const bool ok = mx > 0.0;   // NaN -> false: the row stays zero (:28)
     for (int64_t t = 0; t < T; ++t) {
         double p = 0.0;
@@ -62,11 +94,15 @@ __global__ void k_pdrive_finish(const double *__restrict__ mean_sum, int64_t N, 
     }
 }
 
-int launch_pdrive_meansum(const double *dm, const double *dist, int64_t N, int64_t T, double *mean_sum, cudaStream_t st)
+int launch_pdrive_meansum(const double *dm, const double *dist, double *rdist, int64_t N, int64_t T, double *mean_sum,
+                          cudaStream_t st)
 {
-    const int64_t n = N * T;
-    k_pdrive_meansum<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(dm, dist, N, T, mean_sum);
-    return 1;
+    const int64_t NN = N * N, n = N * T;
+    double2 *dr = reinterpret_cast<double2 *>(rdist);   // [N,N] pairs (dist, 1/dist)
+    k_rdist<<<(unsigned)((NN + 255) / 256), 256, 0, st>>>(dist, NN, dr);
+    (void)n;
+    k_pdrive_meansum<<<(unsigned)(((N + 63) / 64) * T), 64, 0, st>>>(dm, dr, N, T, mean_sum);
+    return 2;
 }
 
 int launch_pdrive_finish(const double *mean_sum, int64_t N, int64_t T, double p_min, double p_max, double e_drive,
@@ -78,10 +114,20 @@ int launch_pdrive_finish(const double *mean_sum, int64_t N, int64_t T, double p_
 
 // ------------------------------------------------------------------------------------------------
 // createpdestin, pass 1 (:10-28): per (i,j) min/max over t (zeros included), then the unnormalised
-// ((m-min)/(max-min))^e_dest.  One thread per (i,j), i fastest: coalesced.  TMAX > 0 keeps the T
-// values in registers (T = 24 in the reference); TMAX == 0 re-reads them.
+// ((m-min)/(max-min))^e_dest.  One thread per (i,j), i fastest: coalesced.  TMAX > 0 keeps the T values in
+// registers (T = 24 in the reference); TMAX == 0 re-reads them.  EK selects Julia's Float64^Int fast paths at
+// compile time (2: x*x -- the reference's e_dest = 2, main.jl:38; 1: x; 3: x*x*x) or the general pow (0).
 // ------------------------------------------------------------------------------------------------
-template <int TMAX>
+template <int EK>
+__device__ __forceinline__ double pow_k(double x, double e)
+{
+    if (EK == 2) return x * x;
+    if (EK == 1) return x;
+    if (EK == 3) return x * x * x;
+    return jl_pow(x, e);
+}
+
+template <int TMAX, int EK>
 __global__ void __launch_bounds__(256) k_pdest_unnorm(const double *__restrict__ dm, int64_t N, int64_t T, double e_dest,
                                                       double *__restrict__ p_dest)
 {
@@ -89,32 +135,40 @@ __global__ void __launch_bounds__(256) k_pdest_unnorm(const double *__restrict__
     const int64_t NN = N * N;
     if (idx >= NN) return;
     double v[TMAX > 0 ? TMAX : 1];
-    double mx, mn;
-    bool has_nan = false;
+    double mx, mn, nan_probe = 0.0;   // fmax/fmin drop NaN; the running sum keeps it (Julia's maximum/minimum propagate NaN)
     if constexpr (TMAX > 0) {
 #pragma unroll
         for (int t = 0; t < TMAX; ++t) v[t] = (t < T) ? __ldg(dm + idx + NN * t) : 0.0;
         mx = mn = v[0];
 #pragma unroll
         for (int t = 0; t < TMAX; ++t)
-            if (t < T) { has_nan |= isnan(v[t]); if (v[t] > mx) mx = v[t]; if (v[t] < mn) mn = v[t]; }
+            if (t < T) { mx = fmax(mx, v[t]); mn = fmin(mn, v[t]); nan_probe += v[t] * 0.0; }
     } else {
         mx = mn = __ldg(dm + idx);
         for (int64_t t = 0; t < T; ++t) {
             const double x = __ldg(dm + idx + NN * t);
-            has_nan |= isnan(x); if (x > mx) mx = x; if (x < mn) mn = x;
+            mx = fmax(mx, x); mn = fmin(mn, x); nan_probe += x * 0.0;
         }
     }
-    if (has_nan) mx = mn = __longlong_as_double(0x7ff8000000000000LL);
+    if (nan_probe != nan_probe) mx = mn = __longlong_as_double(0x7ff8000000000000LL);   // NaN or Inf among the inputs
     const bool ok = mx > 0.0;   // :22
     const double den = mx - mn;
+    const double rden = 1.0 / den;
+    const bool fast = recip_ok(rden);   // else: den is 0 (constant pair -> 0/0 = NaN, :24), Inf or NaN
     if constexpr (TMAX > 0) {
+        if (fast || !ok) {
 #pragma unroll
-        for (int t = 0; t < TMAX; ++t)
-            if (t < T) p_dest[idx + NN * t] = ok ? jl_pow((v[t] - mn) / den, e_dest) : 0.0;   // :24
+            for (int t = 0; t < TMAX; ++t)
+                if (t < T) p_dest[idx + NN * t] = ok ? pow_k<EK>(div_r(v[t] - mn, den, rden), e_dest) : 0.0;   // :24
+        } else {
+#pragma unroll 1
+            for (int64_t t = 0; t < T; ++t)   // re-reads instead of indexing v[] dynamically (keeps v[] in registers)
+                p_dest[idx + NN * t] = pow_k<EK>((__ldg(dm + idx + NN * t) - mn) / den, e_dest);
+        }
     } else {
+#pragma unroll 1
         for (int64_t t = 0; t < T; ++t)
-            p_dest[idx + NN * t] = ok ? jl_pow((__ldg(dm + idx + NN * t) - mn) / den, e_dest) : 0.0;
+            p_dest[idx + NN * t] = ok ? pow_k<EK>((__ldg(dm + idx + NN * t) - mn) / den, e_dest) : 0.0;
     }
 }
 
@@ -151,19 +205,26 @@ __global__ void __launch_bounds__(64) k_pdest_norm(const double *__restrict__ p_
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass 3 (:38-46) fused with the sampling-CDF build.  Each warp owns 32 consecutive origins of one
-// hour; lane = origin, so the loads over j are coalesced and the running sum is accumulated strictly
-// left to right in fp64 -- the association order of the reference's linear scan
-// (src/resampling.jl:38-45), which is what makes destination indices bit-exact.  The CDF is written
-// row-contiguous (destination fastest) through a padded shared-memory transpose.
-//   DIVIDE: p /= norm where norm > 0 and write p back (createpdestin); otherwise p is read-only
-//   (p_dest supplied by the caller, as in the Julia API).
+// pass 3 (:38-46) fused with the sampling-CDF build and its guide table.  Each warp owns 32 consecutive origins of
+// one hour.  Scan phase: lane = origin, so the loads over j are coalesced and the running sum is accumulated
+// strictly left to right in fp64 -- the association order of the reference's linear scan
+// (src/resampling.jl:38-45), which is what makes destination indices bit-exact.  Write phase: through a padded
+// shared-memory transpose, lane = destination, rows are written contiguously (256 B per row and tile) and each
+// entry fills the guide cells it owns: guide[b] = #{j : cdf[j] < b/G}; entry j owns the thresholds b/G in
+// (cdf[j-1], cdf[j]] (exact: G is a power of two), thresholds above the last finite sum see every finite entry,
+// a NaN sum (and everything after it) owns none (common.cuh: cdf_search_guided).
+//   DIVIDE : p /= norm where norm > 0 (createpdestin :40-42); otherwise p is the caller's p_dest (Julia API)
+//   WRITE_P: also write the normalised p back (only when the caller wants p_dest itself)
 // ------------------------------------------------------------------------------------------------
-template <bool DIVIDE>
+__device__ __noinline__ double div_slow(double a, double d) { return a / d; }
+
+template <bool DIVIDE, bool WRITE_P>
 __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, const double *__restrict__ norm, int64_t N,
-                                                   int64_t T, double *__restrict__ cdf, int64_t ldc, uint8_t *__restrict__ rowzero)
+                                                   int64_t T, double *__restrict__ cdf, int64_t ldc, int goff, int G,
+                                                   uint8_t *__restrict__ rowzero)
 {
     __shared__ double tile[4][32][33];
+    __shared__ double carry[4][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i0 = ((int64_t)blockIdx.x * 4 + w) * 32;
     const int64_t t = blockIdx.y;
@@ -172,12 +233,16 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
     const bool live = i < N;
     const int64_t ic = live ? i : N - 1;
     double *p = p_dest + ic + N * N * t;
-    double nf = 1.0;
+    double nf = 1.0, rnf = 1.0;
     bool div = false;
-    if (DIVIDE) { nf = norm[ic + N * t]; div = nf > 0.0; }   // NaN -> skip (:40)
+    if (DIVIDE) { nf = norm[ic + N * t]; div = nf > 0.0; rnf = 1.0 / nf; }   // NaN -> skip (:40)
+    const bool fast = recip_ok(rnf);
     double run = 0.0;
     double *out = cdf + (t * N + i0) * ldc;
-    const int64_t rows = (N - i0 < 32) ? (N - i0) : 32;
+    const int rows = (int)((N - i0 < 32) ? (N - i0) : 32);
+    const double Gd = (double)G;
+    carry[w][lane] = 0.0;
+    __syncwarp();
     for (int64_t j0 = 0; j0 < N; j0 += 32) {
         double v[32];
         if (j0 + 32 <= N) {
@@ -191,70 +256,68 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
         for (int jj = 0; jj < 32; ++jj) {
             double x = v[jj];
             if (DIVIDE && div) {
-                x = x / nf;                                            // :42
-                if (live && j0 + jj < N) p[N * (j0 + jj)] = x;
+                x = fast ? div_r(x, nf, rnf) : div_slow(x, nf);        // :42
+                if (WRITE_P && live && j0 + jj < N) p[N * (j0 + jj)] = x;
             }
             run = run + x;                                             // src/resampling.jl:39
             tile[w][jj][lane] = run;
         }
         __syncwarp();
-        if (j0 + lane < N)
-            for (int64_t r = 0; r < rows; ++r) out[r * ldc + j0 + lane] = tile[w][lane][r];
+        if (j0 + lane < N) {
+            double *orow = out + j0 + lane;
+            const uint16_t jme = (uint16_t)(j0 + lane);
+            const double *tl = &tile[w][lane][0];
+            const double *tp = (lane > 0) ? &tile[w][lane - 1][0] : &carry[w][0];
+            for (int r = 0; r < rows; ++r, orow += ldc) {
+                const double cur = tl[r], prv = tp[r];
+                *orow = cur;
+                if (G > 0 && cur > prv) {                              // NaN never compares greater
+                    const int b_lo = __double2int_rd(fmin(prv * Gd, Gd)) + 1;
+                    const int b_hi = __double2int_rd(fmin(cur * Gd, Gd));
+                    if (b_hi >= b_lo) {
+                        uint16_t *g = reinterpret_cast<uint16_t *>(orow - (j0 + lane) + goff);
+                        for (int b = b_lo; b <= b_hi; ++b) g[b] = jme;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        carry[w][lane] = tile[w][31][lane];
         __syncwarp();
     }
-    if (live) rowzero[t * N + i] = (run == 0.0) ? 1 : 0;               // sum(distribution) == 0 (:35)
-}
-
-// ------------------------------------------------------------------------------------------------
-// Guide ("cut-point") table of every CDF row: guide[b] = #{j : cdf[j] < b/G}, b = 0..G (common.cuh:
-// cdf_search_guided).  One warp per row; entry j owns the thresholds b/G in (cdf[j-1], cdf[j]] (exact: G is a power
-// of two), thresholds above the last finite sum see every finite entry.  A NaN sum (and everything after it) owns none.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_guide_build(double *__restrict__ cdf, int64_t ldc, int goff, int G, int64_t N, int64_t rows)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const double *rowp = cdf + row * ldc;
-    uint16_t *g = reinterpret_cast<uint16_t *>(cdf + row * ldc + goff);
-    const double Gd = (double)G;
-    double carry = 0.0;
-    int64_t n_valid = N;
-    for (int64_t jb = 0; jb < N; jb += 32) {
-        const int64_t j = jb + lane;
-        const bool valid = j < N;
-        const double cur = valid ? rowp[j] : carry;
-        double prev = __shfl_up_sync(0xffffffffu, cur, 1);
-        if (lane == 0) prev = carry;
-        carry = __shfl_sync(0xffffffffu, cur, 31);
-        if (valid && cur > prev) {
-            const double lo_d = prev * Gd, hi_d = cur * Gd;
-            const int b_lo = (lo_d >= Gd) ? G + 1 : (int)floor(lo_d) + 1;
-            const int b_hi = (hi_d >= Gd) ? G : (int)floor(hi_d);
-            for (int b = b_lo; b <= b_hi; ++b) g[b] = (uint16_t)j;
+    if (!live) return;
+    const bool zero = (run == 0.0);
+    rowzero[t * N + i] = zero ? 1 : 0;                                  // sum(distribution) == 0 (:35)
+    if (G > 0 && !zero) {
+        // thresholds above the last finite running sum see every finite entry (rare slow path: a NaN sum)
+        const double *myrow = cdf + (t * N + i) * ldc;
+        int64_t n_valid = N;
+        double last = run;
+        if (run != run) {
+            n_valid = 0;
+            while (n_valid < N && myrow[n_valid] == myrow[n_valid]) ++n_valid;
+            last = n_valid > 0 ? myrow[n_valid - 1] : 0.0;
         }
-        const uint32_t nanmask = __ballot_sync(0xffffffffu, valid && cur != cur);
-        if (nanmask && n_valid == N) n_valid = jb + __ffs(nanmask) - 1;
+        uint16_t *g = reinterpret_cast<uint16_t *>(cdf + (t * N + i) * ldc + goff);
+        for (int b = __double2int_rd(fmin(last * Gd, Gd)) + 1; b <= G; ++b) g[b] = (uint16_t)n_valid;
+        g[0] = 0;
     }
-    const double last = n_valid > 0 ? rowp[n_valid - 1] : 0.0;
-    const double lo_d = last * Gd;
-    const int b_lo = (lo_d >= Gd) ? G + 1 : (int)floor(lo_d) + 1;
-    for (int b = b_lo + lane; b <= G; b += 32) g[b] = (uint16_t)n_valid;
-    if (lane == 0) g[0] = 0;
 }
 
-static void launch_guide(double *cdf, int64_t ldc, int goff, int G, int64_t N, int64_t T, cudaStream_t st)
+template <int EK>
+static void launch_unnorm(const double *dm, int64_t N, int64_t T, double e_dest, double *p_dest, cudaStream_t st)
 {
-    const int64_t rows = N * T;
-    k_guide_build<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(cdf, ldc, goff, G, N, rows);
+    const unsigned g = (unsigned)((N * N + 255) / 256);
+    if (T <= 24) k_pdest_unnorm<24, EK><<<g, 256, 0, st>>>(dm, N, T, e_dest, p_dest);
+    else         k_pdest_unnorm<0, EK><<<g, 256, 0, st>>>(dm, N, T, e_dest, p_dest);
 }
 
 int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double *p_dest, double *norm, cudaStream_t st)
 {
-    const int64_t NN = N * N;
-    const unsigned g = (unsigned)((NN + 255) / 256);
-    if (T <= 24) k_pdest_unnorm<24><<<g, 256, 0, st>>>(dm, N, T, e_dest, p_dest);
-    else         k_pdest_unnorm<0><<<g, 256, 0, st>>>(dm, N, T, e_dest, p_dest);
+    if (e_dest == 2.0) launch_unnorm<2>(dm, N, T, e_dest, p_dest, st);
+    else if (e_dest == 1.0) launch_unnorm<1>(dm, N, T, e_dest, p_dest, st);
+    else if (e_dest == 3.0) launch_unnorm<3>(dm, N, T, e_dest, p_dest, st);
+    else launch_unnorm<0>(dm, N, T, e_dest, p_dest, st);
     k_pdest_norm<<<(unsigned)((N * T + 63) / 64), 64, 0, st>>>(p_dest, N, T, norm);
     return 2;
 }
@@ -263,18 +326,17 @@ int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cd
                           uint8_t *rowzero, cudaStream_t st)
 {
     dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
-    k_cdf_build<false><<<g, 128, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, ldc, rowzero);
-    if (G > 0) launch_guide(cdf, ldc, goff, G, N, T, st);
-    return G > 0 ? 2 : 1;
+    k_cdf_build<false, false><<<g, 128, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, ldc, goff, G, rowzero);
+    return 1;
 }
 
 int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff,
-                         int G, uint8_t *rowzero, cudaStream_t st)
+                         int G, uint8_t *rowzero, int write_p, cudaStream_t st)
 {
     dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
-    k_cdf_build<true><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, rowzero);
-    if (G > 0) launch_guide(cdf, ldc, goff, G, N, T, st);
-    return G > 0 ? 2 : 1;
+    if (write_p) k_cdf_build<true, true><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, goff, G, rowzero);
+    else         k_cdf_build<true, false><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, goff, G, rowzero);
+    return 1;
 }
 
 }  // namespace cpm
