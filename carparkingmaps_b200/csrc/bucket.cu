@@ -1,18 +1,21 @@
-// bucket.cu -- the "bucket" sampler: cars are kept grouped by their current zone, one CTA work item = one
-// zone (or a chunk of a large zone), and the origin's fp64 CDF row is staged in shared memory with a TMA
-// bulk copy (cp.async.bulk + mbarrier), double-buffered across work items.
+// bucket.cu -- the "bucket" sampler: cars are kept grouped by their current zone, so that a CTA works on one
+// zone at a time with the origin's fp64 CDF row (and its guide table) staged in shared memory by a TMA bulk copy
+// (cp.async.bulk + mbarrier).
 //
-// Why (profiles/README.md r1a): with one thread per car in car-id order the 12-probe binary search is a chain
-// of dependent L2/HBM loads under divergence; grouping by origin turns it into shared-memory probes, reads
-// every CDF row once per step (the algorithmic table traffic), and makes the per-zone parked-car
-// histogram free (it IS the bucket size).  Results are identical to the gather sampler and to the reference
-// algorithm because every draw is keyed by (global car id, step), not by processing order.
+// Why (profiles/README.md r1a): with one thread per car in car-id order the categorical draw is a chain of
+// dependent L2/HBM loads under divergence; grouping by origin turns it into shared-memory probes, reads every CDF
+// row once per step (the algorithmic table traffic), and makes the per-zone parked-car histogram free
+// (it IS the bucket size).  Results are identical to the gather sampler and to the reference algorithm because
+// every draw is keyed by (global car id, step), not by processing order.
 //
-// Per step:  k_bucket_sample  (phases 1-3 per car; per-item shared-memory histogram of destinations with
-//                              warp-aggregated atomics; one global atomic per (item, destination) reserves a
-//                              range in the destination bucket)
-//            k_bucket_scatter (prefix-sum of the new bucket sizes, cars move to their new bucket; block 0 also
-//                              writes the next step's work-item list)
+// One step is a counting sort by destination zone with per-CTA histograms (no global atomics on the data path):
+//   k_bucket_sample   CTA g owns a fixed slab of slots [g*S, (g+1)*S); it walks the zone segments inside its slab,
+//                     does phases 1-3 of the reference step per car, ranks every car among the cars OF THIS CTA
+//                     with the same destination (shared-memory histogram), writes (destination, rank) per slot
+//                     and finally its histogram row M[g][*]
+//   k_bucket_colscan  exclusive prefix of M over g per destination (-> where CTA g's cars start inside each
+//                     destination bucket) and the new bucket sizes (= parked cars per zone at the next step)
+//   k_bucket_scatter  prefix sum of the new bucket sizes, then perm_next[start[dest] + M[g][dest] + rank] = car
 // Reference semantics: src/resampling.jl:11-83, src/solveinitialvalueproblem.jl:11-53, src/saveresults.jl:8-17.
 #include "kernels.h"
 
@@ -65,21 +68,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // shared-memory layout of k_bucket_sample
 // ------------------------------------------------------------------------------------------------
 struct SampleSmem {
-    double *row;          // [ldc]   the origin's CDF row (TMA destination)
+    double *row;          // [ldc]   the origin's CDF row + guide table (TMA destination)
     double *srch_u;       // [CH]    u_dest of the compacted drivers
-    uint32_t *hist;       // [N+1]   per-item destination counts, then bucket bases
-    uint16_t *dest_s;     // [CH]    destination bin per car of the item
-    uint16_t *rank_s;     // [CH]    rank among the item's cars with the same destination
-    uint16_t *srch_idx;   // [CH]    slot of each compacted driver
-    uint16_t *touched;    // [CH+2]  destination bins with a non-zero count (so per-item work is O(cars), not O(N))
+    uint32_t *hist;       // [N+1]   cars of this CTA per destination bin (never cleared inside a launch)
+    uint16_t *srch_idx;   // [CH]    chunk-relative slot of each compacted driver
     uint64_t *bar;
-    uint32_t *misc;       // [0] n_search, [1] n_drive, [2] n_touched
+    uint32_t *misc;       // [0],[1] n_search ping-pong counters
 };
 
 __host__ __device__ inline size_t hist_bytes(int64_t N) { return ((size_t)(N + 1) * 4 + 15) / 16 * 16; }
 __host__ __device__ inline size_t sample_smem_bytes(int64_t N, int64_t ldc, int CH)
 {
-    return (size_t)ldc * 8 + (size_t)CH * 8 + hist_bytes(N) + (size_t)CH * 2 * 3 + (size_t)(CH + 8) * 2 + 64;
+    return (size_t)ldc * 8 + (size_t)CH * 8 + hist_bytes(N) + (size_t)CH * 2 + 64;
 }
 
 __device__ __forceinline__ SampleSmem carve(unsigned char *p, int64_t N, int64_t ldc, int CH)
@@ -88,19 +88,25 @@ __device__ __forceinline__ SampleSmem carve(unsigned char *p, int64_t N, int64_t
     s.row = reinterpret_cast<double *>(p); p += (size_t)ldc * 8;
     s.srch_u = reinterpret_cast<double *>(p); p += (size_t)CH * 8;
     s.hist = reinterpret_cast<uint32_t *>(p); p += hist_bytes(N);
-    s.dest_s = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
-    s.rank_s = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
     s.srch_idx = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
-    s.touched = reinterpret_cast<uint16_t *>(p); p += (size_t)(CH + 8) * 2;
     s.bar = reinterpret_cast<uint64_t *>(p); p += 16;
     s.misc = reinterpret_cast<uint32_t *>(p);
     return s;
 }
 
+// largest z in [0, nb) with start[z] <= x  (start is non-decreasing, start[0] = 0, start[nb] = C > x)
+__device__ __forceinline__ int zone_of_slot(const uint32_t *__restrict__ start, int nb, uint32_t x)
+{
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(start + mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // ------------------------------------------------------------------------------------------------
-// k_bucket_sample.  One work item = up to CH cars of one zone.  Several small CTAs per SM run items in
-// different phases, which is what hides the three latencies on an item's critical path (car-id load, CDF-row
-// TMA, the global atomics that reserve ranges in the destination buckets).
+// k_bucket_sample
 // ------------------------------------------------------------------------------------------------
 template <int THREADS, int CH>
 __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int R = CH / THREADS;
     const int64_t N = a.N, NN = a.N * a.N;
-    const int Ni = (int)N;
+    const int Ni = (int)N, NB = Ni + 1;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     SampleSmem s = carve(smem_raw, N, a.ldc, CH);
@@ -118,54 +124,55 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
     const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
     const bool inj = a.rng.mode == 1;
     const int64_t uoff = a.rng.ld * a.step;
-    const int n_items = *a.n_items;
+    uint32_t *const hist = s.hist;
 
     if (tid == 0) { mbar_init(&s.bar[0], 1); fence_mbar_init(); }
-    for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(s.hist)[x] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid < 4) s.misc[tid] = 0u;
+    for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(hist)[x] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 2) s.misc[tid] = 0u;
     __syncthreads();
 
     uint32_t par = 0u;
     unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
+    int pp = 0;   // which n_search counter the current chunk uses
 
-    uint32_t *const hist = s.hist;
-    uint16_t *const touched = s.touched;
-    uint32_t *const n_touched = &s.misc[2];
-    int prev_nt = 0;   // #bins the previous item touched (every thread keeps its own copy: no extra barrier)
+    // this CTA's slab of slots
+    const uint32_t slab_lo = (uint32_t)min((int64_t)blockIdx.x * a.slab, a.C);
+    const uint32_t slab_hi = (uint32_t)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
+    uint32_t pos = slab_lo;
+    int z = (slab_lo < slab_hi) ? zone_of_slot(a.start, NB, slab_lo) : NB;
 
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const int4 it = __ldg(a.items + w);   // x = bin (0..N-1 zone, N = lost), y = first slot, z = #cars
-        const int bin = it.x, lo = it.y, n = it.z;
-        const bool is_zone = bin < Ni;
-        if (is_zone && tid == 0) {   // the row buffer was last read before the previous item's phase-B barrier
-            fence_proxy_async();
-            mbar_expect_tx(&s.bar[0], row_bytes);
-            tma_bulk_g2s(s.row, cdf_t + (int64_t)bin * a.ldc, row_bytes, &s.bar[0]);
+    while (pos < slab_hi) {
+        // zone segment [pos, seg_end) of bin z inside the slab; skip empty zones (usually none)
+        uint32_t z_end = __ldg(a.start + z + 1);
+        if (z_end <= pos) {
+            ++z;
+            z_end = __ldg(a.start + z + 1);
+            if (z_end <= pos) { z = zone_of_slot(a.start, NB, pos); z_end = __ldg(a.start + z + 1); }
         }
-        const int32_t *__restrict__ perm = a.perm_cur + lo;
+        const uint32_t seg_end = min(z_end, slab_hi);
+        const int bin = z;
+        const bool is_zone = bin < Ni;
+        const double pd = is_zone ? __ldg(pd_t + bin) : -1.0;
+        const bool rowzero = is_zone ? (rz_t[bin] != 0) : true;
+        const bool need_row = is_zone && !rowzero;
+        unsigned nd_warp = 0;
 
-        // car ids of all rounds first, so their load latencies overlap each other and the clean-up below
-        int32_t ids[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) { const int k = r * THREADS + tid; ids[r] = (is_zone && k < n) ? __ldg(perm + k) : 0; }
-        // clear the histogram bins the previous item touched (O(cars), not O(N))
-        for (int i = tid; i < prev_nt; i += THREADS) hist[touched[i]] = 0u;
-        __syncthreads();
-
-        if (!is_zone) {
-            // lost cars (zone 0) are carried along: never drive, never counted in a zone
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const int k = r * THREADS + tid;
-                if (k < n) { s.dest_s[k] = (uint16_t)bin; s.rank_s[k] = (uint16_t)k; }
+        for (uint32_t lo = pos; lo < seg_end; lo += CH) {
+            const int n = (int)min((uint32_t)CH, seg_end - lo);
+            const bool first_chunk = lo == pos;
+            if (need_row && first_chunk && tid == 0) {   // the row buffer's last readers passed the barrier that ended phase B
+                fence_proxy_async();
+                mbar_expect_tx(&s.bar[0], row_bytes);
+                tma_bulk_g2s(s.row, cdf_t + (int64_t)bin * a.ldc, row_bytes, &s.bar[0]);
             }
-            if (tid == 0) { hist[bin] = (uint32_t)n; touched[0] = (uint16_t)bin; *n_touched = 1u; lost += (unsigned long long)n; }
-            __syncthreads();
-        } else {
-            const double pd = __ldg(pd_t + bin);
-            const bool rowzero = rz_t[bin] != 0;
-            unsigned nd_warp = 0;
-            // ---- phase A: Bernoulli drive decision for every car of the item (src/resampling.jl:11-22) ----
+            const int32_t *__restrict__ perm = a.perm_cur + lo;
+            uint32_t *__restrict__ out = a.dr + lo;
+            uint32_t *const n_search_ctr = &s.misc[pp];
+
+            // ---- phase A: Bernoulli drive decision for every car of the chunk (src/resampling.jl:11-22) ----
+            int32_t ids[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { const int k = r * THREADS + tid; ids[r] = (is_zone && k < n) ? __ldg(perm + k) : 0; }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r * THREADS >= n) break;          // block-uniform: the ballots below stay convergent
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
                 const bool active = k < n;
                 bool drive = false;
                 double u2 = 0.0;
-                if (active) {
+                if (active && is_zone) {
                     const int64_t id = ids[r];
                     double u1;
                     if (inj) u1 = a.rng.u_drive[id + uoff];
@@ -182,121 +189,79 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
                     if (drive && inj && !rowzero) u2 = a.rng.u_dest[id + uoff];
                 }
                 const bool search = drive && !rowzero;
-                const bool stay = active && !search;                    // parked, or all-zero row (:35-36)
+                const bool stay = active && !search;                    // parked, all-zero row (:35-36), or lost (zone 0)
                 const uint32_t m_drive = __ballot_sync(0xffffffffu, drive);
                 const uint32_t m_stay = __ballot_sync(0xffffffffu, stay);
                 const uint32_t m_s = m_drive & ~m_stay;                 // == ballot(search)
                 nd_warp += __popc(m_drive);
-                // stayers: rank inside the own-zone bin via one warp-aggregated shared atomic;
+                // stayers: rank among this CTA's cars bound for the own zone, one warp-aggregated shared atomic;
                 // searchers: compact (slot, u_dest) so that phase B runs without idle lanes
                 uint32_t base = 0, off = 0;
                 if (lane == 0) {
-                    if (m_stay) {
-                        base = atomicAdd(&hist[bin], (uint32_t)__popc(m_stay));
-                        if (base == 0u) touched[atomicAdd(n_touched, 1u)] = (uint16_t)bin;
-                    }
-                    if (m_s) off = atomicAdd(&s.misc[0], (uint32_t)__popc(m_s));
+                    if (m_stay) base = atomicAdd(&hist[bin], (uint32_t)__popc(m_stay));
+                    if (m_s) off = atomicAdd(n_search_ctr, (uint32_t)__popc(m_s));
                 }
                 base = __shfl_sync(0xffffffffu, base, 0);
                 off = __shfl_sync(0xffffffffu, off, 0);
-                if (stay) { s.dest_s[k] = (uint16_t)bin; s.rank_s[k] = (uint16_t)(base + __popc(m_stay & lt_mask)); }
+                if (stay) out[k] = (uint32_t)bin | ((base + __popc(m_stay & lt_mask)) << 16);
                 if (search) {
                     const uint32_t q = off + __popc(m_s & lt_mask);
                     s.srch_idx[q] = (uint16_t)k;
                     s.srch_u[q] = u2;
                 }
             }
-            if (rowzero && a.with_time && lane == 0) t_hi += 300ull * nd_warp;   // origin == destination: 5 min (:58-59)
-            if (lane == 0 && nd_warp) atomicAdd(&s.misc[1], nd_warp);
+            if (tid == 0) s.misc[pp ^ 1] = 0u;   // the other counter was consumed before the previous barrier
             __syncthreads();
 
             // ---- phase B: categorical destination from the staged CDF row (src/resampling.jl:26-49) ----
-            const int n_search = (int)s.misc[0];
-            mbar_wait(&s.bar[0], par & 1u);   // every thread observes the TMA completion (phase parity stays in step)
-            par ^= 1u;
-            const double *row = s.row;
-            const uint16_t *gd = reinterpret_cast<const uint16_t *>(s.row + a.goff);
-            for (int q0 = 0; q0 < n_search; q0 += THREADS) {   // block-uniform trip count (ballot below)
-                const int q = q0 + tid;
-                const bool act = q < n_search;
-                const int k = act ? s.srch_idx[q] : 0;
-                const double u2 = act ? s.srch_u[q] : 0.0;
-                // guided lower_bound on the staged row; acceptance test as in src/resampling.jl:40 (u = 0, u above the
-                // last entry or a NaN sum -> sentinel 0 = lost)
-                const int32_t d = cdf_search_guided([&](int32_t j) { return row[j]; }, [&](int32_t bb) { return (int32_t)gd[bb]; },
-                                                    Ni, a.G, u2);
-                const bool hit = d > 0;
-                const int pos = d - 1;
-                const int dbin = hit ? pos : Ni;
-                const uint32_t old = act ? atomicAdd(&hist[dbin], 1u) : 1u;
-                // first toucher of a bin appends it to the touched list: one shared atomic per warp, not per lane
-                const uint32_t m_new = __ballot_sync(0xffffffffu, old == 0u);
-                if (m_new) {
-                    uint32_t tbase = 0;
-                    if (lane == 0) tbase = atomicAdd(n_touched, (uint32_t)__popc(m_new));
-                    tbase = __shfl_sync(0xffffffffu, tbase, 0);
-                    if (old == 0u) touched[tbase + __popc(m_new & lt_mask)] = (uint16_t)dbin;
-                }
-                if (!act) continue;
-                s.dest_s[k] = (uint16_t)dbin;
-                s.rank_s[k] = (uint16_t)old;
-                if (a.with_time) {                                   // src/resampling.jl:53-70 (time only: counts mode)
-                    if (dbin == bin) t_hi += 300ull;
-                    else if (hit) {
-                        const int64_t id = __ldg(perm + k);
-                        double u3, u4;
-                        if (inj) u3 = a.rng.u_time[id + uoff];
-                        else philox_pair(a.rng, id, (uint32_t)a.step, 1u, u3, u4);
-                        const int64_t od = (int64_t)bin + N * (int64_t)dbin;
-                        const double mean = __ldg(a.dm + od + NN * a.hour);
-                        double sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
-                        if (sd == 0.0) sd = 0.1 * mean;
-                        fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));
+            const int n_search = (int)*n_search_ctr;
+            if (need_row) {
+                if (first_chunk) { mbar_wait(&s.bar[0], par & 1u); par ^= 1u; }   // every thread observes the TMA completion
+                const double *row = s.row;
+                const uint16_t *gd = reinterpret_cast<const uint16_t *>(s.row + a.goff);
+                for (int q = tid; q < n_search; q += THREADS) {
+                    const int k = s.srch_idx[q];
+                    const double u2 = s.srch_u[q];
+                    // guided lower_bound on the staged row; acceptance test as in src/resampling.jl:40 (u = 0, u above the
+                    // last entry or a NaN sum -> sentinel 0 = lost)
+                    const int32_t d = cdf_search_guided([&](int32_t j) { return row[j]; }, [&](int32_t bb) { return (int32_t)gd[bb]; },
+                                                        Ni, a.G, u2);
+                    const bool hit = d > 0;
+                    const int dbin = hit ? d - 1 : Ni;
+                    const uint32_t rank = atomicAdd(&hist[dbin], 1u);
+                    out[k] = (uint32_t)dbin | (rank << 16);
+                    if (a.with_time) {                                   // src/resampling.jl:53-70 (time only: counts mode)
+                        if (dbin == bin) t_hi += 300ull;
+                        else if (hit) {
+                            const int64_t id = __ldg(perm + k);
+                            double u3, u4;
+                            if (inj) u3 = a.rng.u_time[id + uoff];
+                            else philox_pair(a.rng, id, (uint32_t)a.step, 1u, u3, u4);
+                            const int64_t od = (int64_t)bin + N * (int64_t)dbin;
+                            const double mean = __ldg(a.dm + od + NN * a.hour);
+                            double sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
+                            if (sd == 0.0) sd = 0.1 * mean;
+                            fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));
+                        }
                     }
                 }
             }
             __syncthreads();
+            pp ^= 1;
         }
-
-        // ---- phase C: reserve a range in every touched destination bucket (one global atomic per item x destination) ----
-        {
-            const int nt = (int)*n_touched;
-            prev_nt = nt;
-            // batches of CB atomics per thread are issued back to back so that their round trips overlap
-            constexpr int CB = 4;
-            for (int i0 = 0; i0 < nt; i0 += THREADS * CB) {
-                int b[CB];
-                uint32_t c[CB];
-#pragma unroll
-                for (int u = 0; u < CB; ++u) {
-                    const int i = i0 + u * THREADS + tid;
-                    b[u] = (i < nt) ? (int)touched[i] : -1;
-                    c[u] = (b[u] >= 0) ? hist[b[u]] : 0u;
-                }
-#pragma unroll
-                for (int u = 0; u < CB; ++u) if (b[u] >= 0) c[u] = atomicAdd(a.cnt_next + b[u], c[u]);
-#pragma unroll
-                for (int u = 0; u < CB; ++u) if (b[u] >= 0) hist[b[u]] = c[u];
-            }
-            if (tid == 0 && is_zone && s.misc[1]) atomicAdd(a.drv + bin, s.misc[1]);   // src/saveresults.jl:13-15
-        }
-        __syncthreads();
-
-        // ---- phase D: destination bin and position inside it, per slot (coalesced) ----
-        if (tid == 0) { s.misc[0] = 0u; s.misc[1] = 0u; *n_touched = 0u; }   // all were consumed before the barrier above
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int k = r * THREADS + tid;
-            if (k < n) {
-                const int db = s.dest_s[k];
-                a.dest[lo + k] = (uint16_t)db;
-                a.pos[lo + k] = hist[db] + s.rank_s[k];
-            }
-        }
-        __syncthreads();
+        if (is_zone) {
+            if (rowzero && a.with_time && lane == 0) t_hi += 300ull * nd_warp;   // origin == destination: 5 min (:58-59)
+            if (lane == 0 && nd_warp) atomicAdd(a.drv + bin, nd_warp);             // src/saveresults.jl:13-15
+        } else if (tid == 0) lost += (unsigned long long)(seg_end - pos);
+        pos = seg_end;
+        ++z;
     }
 
-    // driving-time and lost-car totals: integer block reduction, two global atomics per CTA
+    // this CTA's histogram row: M[g][bin] = cars of slab g bound for bin
+    uint32_t *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
+    for (int x = tid; x < NB; x += THREADS) Mrow[x] = hist[x];
+
+    // driving-time and lost-car totals: integer block reduction, a few global atomics per CTA
     __shared__ unsigned long long red[3];
     if (tid < 3) red[tid] = 0ull;
     __syncthreads();
@@ -316,10 +281,70 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// prefix sum of bucket sizes + work-item list (device function shared by k_bucket_items and k_bucket_scatter)
+// k_bucket_colscan: M[g][b] <- sum_{g' < g} M[g'][b] (exclusive, in place); cnt_next[b] <- sum_g M[g][b].
+// One CTA per 32 destination columns: 32 x 32 threads, each sums / rescans a stripe of slabs; coalesced 128 B rows.
+// ------------------------------------------------------------------------------------------------
+template <int PER>   // PER >= ceil(G / 32): the stripe of one thread lives in registers (one pass over M)
+__global__ void __launch_bounds__(1024) k_bucket_colscan(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
+{
+    __shared__ uint32_t ps[32][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
+    const int per = (G + 31) / 32;
+    const int g0 = min(G, part * per), g1 = min(G, g0 + per);
+    const bool live = c < NB;
+    uint32_t v[PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+        const int g = g0 + u;
+        v[u] = (live && g < g1) ? M[(size_t)g * NB + c] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < PER; ++u) sum += v[u];
+    ps[part][threadIdx.x & 31] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int p = 0; p < part; ++p) run += ps[p][threadIdx.x & 31];
+    if (live) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const int g = g0 + u;
+            if (g < g1) M[(size_t)g * NB + c] = run;
+            run += v[u];
+        }
+        if (part == 31) cnt_next[c] = run;   // the last stripe ends with the column total
+    }
+}
+
+// general fallback (any G): two passes over the stripe
+__global__ void __launch_bounds__(1024) k_bucket_colscan_any(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
+{
+    __shared__ uint32_t ps[32][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
+    const int per = (G + 31) / 32;
+    const int g0 = min(G, part * per), g1 = min(G, g0 + per);
+    const bool live = c < NB;
+    uint32_t sum = 0;
+    if (live) for (int g = g0; g < g1; ++g) sum += M[(size_t)g * NB + c];
+    ps[part][threadIdx.x & 31] = sum;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int p = 0; p < part; ++p) run += ps[p][threadIdx.x & 31];
+    if (live) {
+        for (int g = g0; g < g1; ++g) {
+            const size_t k = (size_t)g * NB + c;
+            const uint32_t v = M[k];
+            M[k] = run;
+            run += v;
+        }
+        if (part == 31) cnt_next[c] = run;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // exclusive block scan of v[0..n) in place (v in shared memory); returns the total.  blockDim.x <= 1024.
-__device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot /*[32]*/)
+// ------------------------------------------------------------------------------------------------
+__device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot /*[33]*/)
 {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const int per = (n + nt - 1) / nt;
@@ -352,61 +377,64 @@ __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot 
     return warp_tot[32];
 }
 
-// start[] (shared, NB+1 entries incl. total) must already hold the exclusive scan of cnt[]
-__device__ void write_items(const uint32_t *__restrict__ cnt, const uint32_t *start, uint32_t *itoff, uint32_t *warp_tot,
-                            int NB, uint32_t chunk, int4 *__restrict__ items, int32_t *__restrict__ n_items)
-{
-    for (int x = threadIdx.x; x < NB; x += blockDim.x) itoff[x] = (cnt[x] + chunk - 1) / chunk;
-    __syncthreads();
-    const uint32_t total = block_exclusive_scan(itoff, NB, warp_tot);
-    for (int x = threadIdx.x; x < NB; x += blockDim.x) {
-        const uint32_t c = cnt[x];
-        uint32_t o = itoff[x];
-        for (uint32_t j = 0; j * chunk < c; ++j)
-            items[o + j] = make_int4(x, (int)(start[x] + j * chunk), (int)min(chunk, c - j * chunk), 0);
-    }
-    if (threadIdx.x == 0) *n_items = (int32_t)total;
-}
-
-// day start / stand-alone: start[] and the item list from cnt[]
-__global__ void __launch_bounds__(1024) k_bucket_items(const uint32_t *__restrict__ cnt, int NB, uint32_t chunk,
-                                                       uint32_t *__restrict__ start_out, int4 *__restrict__ items,
-                                                       int32_t *__restrict__ n_items)
-{
-    extern __shared__ uint32_t sm[];   // start[NB] | itoff[NB] | warp_tot[33]
-    uint32_t *start = sm, *itoff = sm + NB, *warp_tot = sm + 2 * NB;
-    for (int x = threadIdx.x; x < NB; x += blockDim.x) start[x] = cnt[x];
-    __syncthreads();
-    block_exclusive_scan(start, NB, warp_tot);
-    if (start_out) for (int x = threadIdx.x; x < NB; x += blockDim.x) start_out[x] = start[x];
-    write_items(cnt, start, itoff, warp_tot, NB, chunk, items, n_items);
-}
-
 // ------------------------------------------------------------------------------------------------
-// k_bucket_scatter: cars move to their destination bucket (state update, src/resampling.jl:81-83)
+// k_bucket_scatter: cars move to their destination bucket (state update, src/resampling.jl:81-83).
+// CTA g handles the slab CTA g of k_bucket_sample handled: off[b] = start_next[b] + M[g][b].
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_bucket_scatter(const ScatterArgs a)
+__global__ void __launch_bounds__(256) k_bucket_scatter(const ScatterArgs a)
 {
-    extern __shared__ uint32_t sm[];   // start[NB] | itoff[NB] (block 0) | warp_tot[33]
+    extern __shared__ uint32_t sm[];   // off[NB] | warp_tot[33]
     const int NB = a.NB;
-    uint32_t *start = sm, *itoff = sm + NB, *warp_tot = sm + 2 * NB;
-    for (int x = threadIdx.x; x < NB; x += blockDim.x) start[x] = a.cnt_next[x];
-    __syncthreads();
-    block_exclusive_scan(start, NB, warp_tot);
-    for (int64_t sl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; sl < a.C; sl += (int64_t)gridDim.x * blockDim.x) {
-        const int db = a.dest[sl];
-        const int32_t id = a.perm_cur[sl];
-        a.perm_next[start[db] + a.pos[sl]] = id;
-        if (a.zone_out) a.zone_out[id] = (db < NB - 1) ? db + 1 : 0;   // last step: car-id indexed state
+    uint32_t *off = sm, *warp_tot = sm + NB;
+    const uint32_t *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
+    constexpr int PRE = 4;   // independent loads in flight per thread
+    for (int x0 = 0; x0 < NB; x0 += PRE * 256) {
+        uint32_t c[PRE];
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; c[u] = (x < NB) ? __ldg(a.cnt_next + x) : 0u; }
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; if (x < NB) off[x] = c[u]; }
     }
-    if (blockIdx.x == 0 && a.items) {
-        __syncthreads();
-        write_items(a.cnt_next, start, itoff, warp_tot, NB, (uint32_t)a.chunk, a.items, a.n_items);
+    __syncthreads();
+    const uint32_t total = block_exclusive_scan(off, NB, warp_tot);
+    if (blockIdx.x == 0) {   // bucket starts of the next step, for the next k_bucket_sample
+        for (int x = threadIdx.x; x < NB; x += blockDim.x) a.start_next[x] = off[x];
+        if (threadIdx.x == 0) a.start_next[NB] = total;
+    }
+    for (int x0 = 0; x0 < NB; x0 += PRE * 256) {
+        uint32_t c[PRE];
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; c[u] = (x < NB) ? __ldg(Mrow + x) : 0u; }
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; if (x < NB) off[x] += c[u]; }
+    }
+    __syncthreads();
+    const int lo = (int)min((int64_t)blockIdx.x * a.slab, a.C), hi = (int)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
+    const uint32_t *__restrict__ dr = a.dr;
+    const int32_t *__restrict__ pc = a.perm_cur;
+    for (int s0 = lo; s0 < hi; s0 += PRE * 256) {
+        uint32_t v[PRE];
+        int32_t id[PRE];
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+            const int sl = s0 + u * 256 + threadIdx.x;
+            v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
+            id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < PRE; ++u) {
+            const int sl = s0 + u * 256 + threadIdx.x;
+            if (sl < hi) {
+                const int db = (int)(v[u] & 0xffffu);
+                a.perm_next[off[db] + (v[u] >> 16)] = id[u];
+                if (a.zone_out) a.zone_out[id[u]] = (db < NB - 1) ? db + 1 : 0;   // last step: car-id indexed state
+            }
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// bucketize a car-id indexed zone array (day start) and its inverse
+// bucketize a car-id indexed zone array (day start)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int zone_bin(int32_t z, int NB) { return (z >= 1 && z < NB) ? z - 1 : NB - 1; }
 
@@ -419,6 +447,18 @@ __global__ void __launch_bounds__(256) k_bucket_hist(const int32_t *__restrict__
         const uint32_t grp = __match_any_sync(0xffffffffu, b);       // lanes with the same bin
         if (act && (threadIdx.x & 31) == (__ffs(grp) - 1)) atomicAdd(cnt + b, (uint32_t)__popc(grp));
     }
+}
+
+// start[0..NB] = exclusive scan of cnt[0..NB) (+ total)
+__global__ void __launch_bounds__(1024) k_bucket_start(const uint32_t *__restrict__ cnt, int NB, uint32_t *__restrict__ start)
+{
+    extern __shared__ uint32_t sm[];   // v[NB] | warp_tot[33]
+    uint32_t *v = sm, *warp_tot = sm + NB;
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) v[x] = cnt[x];
+    __syncthreads();
+    const uint32_t total = block_exclusive_scan(v, NB, warp_tot);
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) start[x] = v[x];
+    if (threadIdx.x == 0) start[NB] = total;
 }
 
 __global__ void __launch_bounds__(256) k_bucket_place(const int32_t *__restrict__ zone, int64_t C, int NB,
@@ -437,12 +477,6 @@ __global__ void __launch_bounds__(256) k_bucket_place(const int32_t *__restrict_
         base = __shfl_sync(0xffffffffu, base, leader);
         if (act) perm[start[b] + base + __popc(grp & lt)] = (int32_t)i;
     }
-}
-
-// fleet_init directly in bucketed form: car i sits in zone i/cpz + 1 -> perm = identity, cnt = histogram of that map
-__global__ void __launch_bounds__(256) k_bucket_init_sorted(int32_t *__restrict__ perm, int64_t C)
-{
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < C; i += (int64_t)gridDim.x * blockDim.x) perm[i] = (int32_t)i;
 }
 
 // counts in the public layout: parking/driving uint32 [N, n_steps] from the bucket arrays with stride NB = N + 1
@@ -465,27 +499,35 @@ __global__ void k_finalize_time(const unsigned long long *hi, const unsigned lon
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-// Two shapes: small CTAs (256 threads, items of 1,024 cars) so that four fit on an SM when the CDF row is small
-// (N up to ~3,000), otherwise 512 threads / 2,048 cars with as many CTAs as shared memory allows.
+// Two shapes: small CTAs (256 threads, chunks of 1,024 cars) so that four fit on an SM when the CDF row is
+// small (N up to ~3,000), otherwise 512 threads / 2,048 cars with as many CTAs as shared memory allows.
 static int bucket_shape(int64_t N, int64_t ldc, size_t *smem_out, int *ctas_out)
 {
     const size_t small = sample_smem_bytes(N, ldc, 1024), big = sample_smem_bytes(N, ldc, 2048);
     const size_t sm_total = 227 * 1024;
-    if (4 * (small + 1024) <= sm_total) { *smem_out = small; *ctas_out = (int)(sm_total / (small + 1024)); return 1; }
-    if (big + 1024 <= sm_total) { *smem_out = big; *ctas_out = (int)(sm_total / (big + 1024)); return 2; }
+    if (4 * (small + 1024) <= sm_total) { *smem_out = small; *ctas_out = 4; return 1; }   // 4 x 256 x 64 regs fill the register file
+    if (big + 1024 <= sm_total) { *smem_out = big; *ctas_out = (2 * (big + 1024) <= sm_total) ? 2 : 1; return 2; }
     return 0;
-}
-
-int bucket_chunk(int64_t N, int64_t ldc)
-{
-    size_t smem; int ctas;
-    const int shape = bucket_shape(N, ldc, &smem, &ctas);
-    return shape == 1 ? 1024 : shape == 2 ? 2048 : 0;
 }
 
 bool bucket_supported(int64_t N, int64_t ldc)
 {
-    return N + 1 <= 65535 && bucket_chunk(N, ldc) != 0;
+    size_t smem; int ctas;
+    return N + 1 <= 65535 && bucket_shape(N, ldc, &smem, &ctas) != 0;
+}
+
+// number of slabs (= CTAs of k_bucket_sample / k_bucket_scatter) and slab size: one resident wave, more only when a
+// slab would exceed the 16-bit rank range
+void bucket_grid(int64_t N, int64_t ldc, int64_t C, int *G_out, int64_t *slab_out)
+{
+    size_t smem = 0; int ctas = 1;
+    bucket_shape(N, ldc, &smem, &ctas);
+    int64_t G = (int64_t)kSMs * ctas;
+    const int64_t min_G = (C + 65534) / 65535;
+    if (G < min_G) G = min_G;
+    if (G > C) G = C > 0 ? C : 1;
+    *G_out = (int)G;
+    *slab_out = (C + G - 1) / G;
 }
 
 // opt in to > 48 KB of dynamic shared memory, raising the per-kernel limit only when a launch needs more
@@ -498,52 +540,51 @@ static void ensure_smem(K kernel, size_t bytes, size_t &granted)
     }
 }
 
-int launch_bucket_sample(const BucketArgs &a, cudaStream_t st)
+int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
 {
     size_t smem = 0; int ctas = 0;
     const int shape = bucket_shape(a.N, a.ldc, &smem, &ctas);
     static size_t granted[3] = {0, 0, 0};
     if (shape == 1) {
-        if (ctas > 8) ctas = 8;
         ensure_smem(k_bucket_sample<256, 1024>, smem, granted[1]);
-        k_bucket_sample<256, 1024><<<kSMs * ctas, 256, smem, st>>>(a);
+        k_bucket_sample<256, 1024><<<G, 256, smem, st>>>(a);
     } else if (shape == 2) {
-        if (ctas > 4) ctas = 4;
         ensure_smem(k_bucket_sample<512, 2048>, smem, granted[2]);
-        k_bucket_sample<512, 2048><<<kSMs * ctas, 512, smem, st>>>(a);
+        k_bucket_sample<512, 2048><<<G, 512, smem, st>>>(a);
     } else return -1;
     return 1;
 }
 
-static size_t scan_smem(int NB) { return ((size_t)2 * NB + 40) * sizeof(uint32_t); }
-
-int launch_bucket_items(const uint32_t *cnt, int NB, int chunk, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st)
+int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaStream_t st)
 {
-    static size_t granted = 48 * 1024;
-    ensure_smem(k_bucket_items, scan_smem(NB), granted);
-    k_bucket_items<<<1, 1024, scan_smem(NB), st>>>(cnt, NB, (uint32_t)chunk, start_out, items, n_items);
+    const int per = (G + 31) / 32, blocks = (NB + 31) / 32;
+    if (per <= 20) k_bucket_colscan<20><<<blocks, 1024, 0, st>>>(M, G, NB, cnt_next);
+    else if (per <= 40) k_bucket_colscan<40><<<blocks, 1024, 0, st>>>(M, G, NB, cnt_next);
+    else k_bucket_colscan_any<<<blocks, 1024, 0, st>>>(M, G, NB, cnt_next);
     return 1;
 }
 
-int launch_bucket_scatter(const ScatterArgs &a, cudaStream_t st)
+static size_t scan_smem(int NB) { return ((size_t)NB + 40) * sizeof(uint32_t); }
+
+int launch_bucket_scatter(const ScatterArgs &a, int G, cudaStream_t st)
 {
     static size_t granted = 48 * 1024;
     ensure_smem(k_bucket_scatter, scan_smem(a.NB), granted);
-    int64_t blocks = (a.C + 1023) / 1024;
-    if (blocks > kSMs * 2) blocks = kSMs * 2;
-    k_bucket_scatter<<<(unsigned)blocks, 1024, scan_smem(a.NB), st>>>(a);
+    k_bucket_scatter<<<G, 256, scan_smem(a.NB), st>>>(a);
     return 1;
 }
 
-int launch_bucketize(const int32_t *zone, int64_t C, int NB, int chunk, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
-                     int32_t *perm, int4 *items, int32_t *n_items, cudaStream_t st)
+int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start, uint32_t *cursor_tmp,
+                     int32_t *perm, cudaStream_t st)
 {
     cudaMemsetAsync(cnt0, 0, (size_t)NB * sizeof(uint32_t), st);
     cudaMemsetAsync(cursor_tmp, 0, (size_t)NB * sizeof(uint32_t), st);
     const int g = sampler_grid(C);
     k_bucket_hist<<<g, 256, 0, st>>>(zone, C, NB, cnt0);
-    launch_bucket_items(cnt0, NB, chunk, start_tmp, items, n_items, st);
-    k_bucket_place<<<g, 256, 0, st>>>(zone, C, NB, start_tmp, cursor_tmp, perm);
+    static size_t granted = 48 * 1024;
+    ensure_smem(k_bucket_start, scan_smem(NB), granted);
+    k_bucket_start<<<1, 1024, scan_smem(NB), st>>>(cnt0, NB, start);
+    k_bucket_place<<<g, 256, 0, st>>>(zone, C, NB, start, cursor_tmp, perm);
     return 3;
 }
 

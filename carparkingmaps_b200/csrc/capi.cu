@@ -576,50 +576,48 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     const int64_t N = city->N, C = f->C;
     const int NB = (int)N + 1;
     const int64_t S = o->n_steps;
-    const int chunk = bucket_chunk(N, city->ldc);
-    const size_t max_items = (size_t)NB + (size_t)(C / chunk) + 2;
+    int G = 0; int64_t slab = 0;
+    bucket_grid(N, city->ldc, C, &G, &slab);
     TRY(f->perm[0].ensure((size_t)C * 4)); TRY(f->perm[1].ensure((size_t)C * 4));
-    TRY(f->dest.ensure((size_t)C * 4)); TRY(f->pos.ensure((size_t)C * 4));
+    TRY(f->dest.ensure((size_t)C * 4));                                   // (destination, rank) per slot
+    TRY(f->pos.ensure((size_t)G * NB * 4));                               // per-slab destination histograms
     TRY(f->bcnt.ensure((size_t)(S + 1) * NB * 4)); TRY(f->bdrv.ensure((size_t)S * NB * 4));
-    TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)NB * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
-    TRY(f->items.ensure(max_items * sizeof(int4))); TRY(f->n_items.ensure(16));
-    uint32_t *bcnt = f->bcnt.as<uint32_t>(), *bdrv = f->bdrv.as<uint32_t>();
-    CU(cudaMemsetAsync(bcnt, 0, (size_t)(S + 1) * NB * 4, ctx->st));
+    TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
+    uint32_t *bcnt = f->bcnt.as<uint32_t>(), *bdrv = f->bdrv.as<uint32_t>(), *start = f->start_tmp.as<uint32_t>();
     CU(cudaMemsetAsync(bdrv, 0, (size_t)S * NB * 4, ctx->st));
     if (f->bucket_valid && f->bucket_N == N) {
-        // still grouped from the previous day: bucket sizes and the work-item list are current
+        // still grouped from the previous day: bucket sizes and bucket starts are current
         CU(cudaMemcpyAsync(bcnt, f->cnt_cur.p, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
     } else {
         if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
         f->cur = 0;
-        LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), C, NB, chunk, bcnt, f->start_tmp.as<uint32_t>(), f->cursor_tmp.as<uint32_t>(),
-                                     f->perm[0].as<int32_t>(), f->items.as<int4>(), f->n_items.as<int32_t>(), ctx->st));
+        LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), C, NB, bcnt, start, f->cursor_tmp.as<uint32_t>(),
+                                     f->perm[0].as<int32_t>(), ctx->st));
     }
     Scalars *sc = f->scalars.as<Scalars>();
     BucketArgs a;
     memset(&a, 0, sizeof a);
     a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
     a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
-    a.N = N; a.T_tab = city->T; a.C = C;
-    a.dest = f->dest.as<uint16_t>(); a.pos = f->pos.as<uint32_t>();
+    a.N = N; a.T_tab = city->T; a.C = C; a.slab = slab;
+    a.start = start; a.dr = f->dest.as<uint32_t>(); a.M = f->pos.as<uint32_t>();
     a.with_time = o->with_time;
     a.rng = make_rng(o->rng, C);
-    a.items = f->items.as<int4>(); a.n_items = f->n_items.as<int32_t>();
     a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo; a.lost = &sc->lost;
     ScatterArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.NB = NB; sa.dest = a.dest; sa.pos = a.pos; sa.C = C; sa.chunk = chunk;
-    sa.items = f->items.as<int4>(); sa.n_items = f->n_items.as<int32_t>();
+    sa.NB = NB; sa.dr = a.dr; sa.C = C; sa.slab = slab; sa.M = a.M; sa.start_next = start;
     TRY(profile_open(ctx, S));
     for (int64_t s = 0; s < S; ++s) {
         a.step = s; a.hour = s / o->steps_per_hour;
         a.perm_cur = f->perm[f->cur].as<int32_t>();
-        a.cnt_next = bcnt + (size_t)(s + 1) * NB;
         a.drv = bdrv + (size_t)s * NB;
-        LAUNCH(ctx, launch_bucket_sample(a, ctx->st));
-        sa.cnt_next = a.cnt_next; sa.perm_cur = a.perm_cur; sa.perm_next = f->perm[f->cur ^ 1].as<int32_t>();
+        LAUNCH(ctx, launch_bucket_sample(a, G, ctx->st));
+        uint32_t *cnt_next = bcnt + (size_t)(s + 1) * NB;
+        LAUNCH(ctx, launch_bucket_colscan(a.M, G, NB, cnt_next, ctx->st));
+        sa.cnt_next = cnt_next; sa.perm_cur = a.perm_cur; sa.perm_next = f->perm[f->cur ^ 1].as<int32_t>();
         sa.zone_out = (s == S - 1) ? f->zone.as<int32_t>() : nullptr;
-        LAUNCH(ctx, launch_bucket_scatter(sa, ctx->st));
+        LAUNCH(ctx, launch_bucket_scatter(sa, G, ctx->st));
         f->cur ^= 1;
     }
     TRY(profile_close(ctx));

@@ -66,31 +66,29 @@ struct BucketArgs {
     const double *p_drive; const double *cdf; int64_t ldc; int32_t goff, G; const uint8_t *rowzero; const double *dm;
     int64_t N, T_tab;
     const int32_t *perm_cur;   // [C] car ids grouped by zone bin
-    uint16_t *dest;            // [C] destination bin per slot (N = lost)
-    uint32_t *pos;             // [C] position inside the destination bucket
-    int64_t C, step, hour;
+    const uint32_t *start;     // [N+2] first slot of every bin (bin N = lost cars), start[N+1] = C
+    uint32_t *dr;              // [C] per slot: destination bin (low 16 bits) | rank among the slab's cars with that destination
+    uint32_t *M;               // [G][N+1] per-slab destination histogram
+    int64_t C, slab, step, hour;
     int32_t with_time;
     RngDev rng;
-    uint32_t *cnt_next;        // [N+1] bucket sizes of step+1 (accumulated)
     uint32_t *drv;             // [N+1] driving cars per origin of this step
-    const int4 *items;         // (bin, first slot, #cars, -)
-    const int32_t *n_items;
     unsigned long long *t_hi, *t_lo, *lost;
 };
 struct ScatterArgs {
-    const uint32_t *cnt_next; int NB;
-    const uint16_t *dest; const uint32_t *pos; const int32_t *perm_cur; int32_t *perm_next; int64_t C;
+    const uint32_t *cnt_next; int NB;   // new bucket sizes (written by the column scan)
+    const uint32_t *dr; const int32_t *perm_cur; int32_t *perm_next; int64_t C, slab;
+    const uint32_t *M;         // [G][N+1] exclusive prefix over slabs
+    uint32_t *start_next;      // [N+2] written by block 0
     int32_t *zone_out;         // nullable: car-id indexed zone (written on the last step of a day)
-    int4 *items; int32_t *n_items;   // next step's work items (written by block 0)
-    int chunk;                 // cars per work item
 };
 bool bucket_supported(int64_t N, int64_t ldc);
-int bucket_chunk(int64_t N, int64_t ldc);   // cars per work item for this table size (0 = unsupported)
-int launch_bucket_sample(const BucketArgs &a, cudaStream_t st);
-int launch_bucket_scatter(const ScatterArgs &a, cudaStream_t st);
-int launch_bucket_items(const uint32_t *cnt, int NB, int chunk, uint32_t *start_out, int4 *items, int32_t *n_items, cudaStream_t st);
-int launch_bucketize(const int32_t *zone, int64_t C, int NB, int chunk, uint32_t *cnt0, uint32_t *start_tmp, uint32_t *cursor_tmp,
-                     int32_t *perm, int4 *items, int32_t *n_items, cudaStream_t st);
+void bucket_grid(int64_t N, int64_t ldc, int64_t C, int *G_out, int64_t *slab_out);
+int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st);
+int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaStream_t st);
+int launch_bucket_scatter(const ScatterArgs &a, int G, cudaStream_t st);
+int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start, uint32_t *cursor_tmp,
+                     int32_t *perm, cudaStream_t st);
 int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
                                 uint32_t *driving, cudaStream_t st);
 int launch_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out, cudaStream_t st);
