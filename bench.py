@@ -34,6 +34,9 @@ WORKLOADS = {
     "cfg2": (2400, 1000, 24),    # Melbourne-scale synthetic city (the config the metric is quoted on)
 }
 PARAMS = dict(e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9)   # main.jl:37-40
+# dram__bytes_read.sum + dram__bytes_write.sum per k_bucket_sample launch, from the committed `ncu --set full` capture
+# (profiles/README.md); None where no capture exists
+NCU_TRAFFIC_BYTES = {"cfg2": None}
 
 
 def measured_peak():
@@ -274,6 +277,32 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
         e2e_ms = e0.elapsed_time(e1)
         parking, traffic, A_drive, lost = out
 
+        # ---- e2e through the row interface (createdatamatrix on the device, src/createdatamatrix.jl:8-23): only
+        #      meaningful for sparse inputs, where the CSV rows are much smaller than the dense array ----
+        e2e_rows = None
+        if args.density < 0.5 and world == 1:
+            ii, jj, tt = np.nonzero(dm_F[:, :, :, 0])
+            cols = [((ii + 1) % N).astype(np.int32), ((jj + 1) % N).astype(np.int32), ((tt + 1) % 24).astype(np.int32)]
+            vals = [np.ascontiguousarray(dm_F[ii, jj, tt, 0]), np.ascontiguousarray(dm_F[ii, jj, tt, 1])]
+
+            def rows_step():
+                city.upload_rows(cols[0], cols[1], cols[2], vals[0], vals[1], dist_F)
+                return sample_dataset(city, fleet, **kw)
+
+            out_r = rows_step()
+            assert np.array_equal(out_r[0], parking) and out_r[2] == A_drive, "row ingest changed the result"
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(e2e_steps):
+                rows_step()
+            r1.record(stream)
+            barrier()
+            rows_ms = r0.elapsed_time(r1)
+            e2e_rows = {"value": trans_per_step * e2e_steps / (rows_ms * 1e-3), "unit": "transitions/s",
+                        "h2d_bytes_per_step": int(len(ii) * 28 + n_dist * 8), "rows": int(len(ii)), "ms_per_step": rows_ms / e2e_steps,
+                        "note": "pageable host columns (sourceid, dstid, hod, mean, std) scattered on the device"}
+
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist_.all_reduce(t, op=dist_.ReduceOp.MAX)
@@ -294,10 +323,15 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             "config": workload_config(args, N, cpz, T),
             "e2e": {"value": e2e_value, "unit": "transitions/s", "h2d_bytes_per_step": (n_dm + n_dist) * 8,
                     "d2h_bytes_per_step": (N * T + T) * 8 + 16, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "e2e_rows": e2e_rows,
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "k_step_gather (per-step sampling kernel)", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            # dominant kernel: k_bucket_sample (one launch = one HMM step over all C cars).  Its launches are bracketed
+            # one by one with CUDA events on the library's stream inside the timed region; `traffic` is the ncu
+            # dram__bytes_read+write per launch of the committed capture (profiles/README.md), not a live figure.
+            "roofline": {"bound": "hbm", "kernel": "k_bucket_sample (per-step sampling kernel)", "achieved": achieved,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                          "bytes_per_transition": B, "transitions_per_launch": C_, "avg_launch_ms": avg_launch_ms,
                          "launches_timed": int(step_launches), "kernel_share_of_step": step_ms / ms},
             "result_check": {"A_drive": A_drive, "lost": int(lost), "parking_sum_t1": float(parking[:, 0].sum())},

@@ -383,17 +383,34 @@ __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bucket_scatter(const ScatterArgs a)
 {
-    extern __shared__ uint32_t sm[];   // off[NB] | warp_tot[33]
+    extern __shared__ uint32_t sm[];   // off[NB] | mrow[NB] | warp_tot[33]
     const int NB = a.NB;
-    uint32_t *off = sm, *warp_tot = sm + NB;
+    uint32_t *off = sm, *mrow = sm + NB, *warp_tot = sm + 2 * NB;
     const uint32_t *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
-    constexpr int PRE = 4;   // independent loads in flight per thread
+    const int lo = (int)min((int64_t)blockIdx.x * a.slab, a.C), hi = (int)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
+    const uint32_t *__restrict__ dr = a.dr;
+    const int32_t *__restrict__ pc = a.perm_cur;
+    // every global load this CTA needs is issued up front (slot data of the first batch, bucket sizes, its M row),
+    // so the prefix sum below runs under their latency
+    constexpr int PS = 16, PRE = 4;
+    uint32_t v[PS];
+    int32_t id[PS];
+#pragma unroll
+    for (int u = 0; u < PS; ++u) {
+        const int sl = lo + u * 256 + threadIdx.x;
+        v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
+        id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
+    }
     for (int x0 = 0; x0 < NB; x0 += PRE * 256) {
-        uint32_t c[PRE];
+        uint32_t c[PRE], m[PRE];
 #pragma unroll
-        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; c[u] = (x < NB) ? __ldg(a.cnt_next + x) : 0u; }
+        for (int u = 0; u < PRE; ++u) {
+            const int x = x0 + u * 256 + threadIdx.x;
+            c[u] = (x < NB) ? __ldg(a.cnt_next + x) : 0u;
+            m[u] = (x < NB) ? __ldg(Mrow + x) : 0u;
+        }
 #pragma unroll
-        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; if (x < NB) off[x] = c[u]; }
+        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; if (x < NB) { off[x] = c[u]; mrow[x] = m[u]; } }
     }
     __syncthreads();
     const uint32_t total = block_exclusive_scan(off, NB, warp_tot);
@@ -401,28 +418,19 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const ScatterArgs a)
         for (int x = threadIdx.x; x < NB; x += blockDim.x) a.start_next[x] = off[x];
         if (threadIdx.x == 0) a.start_next[NB] = total;
     }
-    for (int x0 = 0; x0 < NB; x0 += PRE * 256) {
-        uint32_t c[PRE];
-#pragma unroll
-        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; c[u] = (x < NB) ? __ldg(Mrow + x) : 0u; }
-#pragma unroll
-        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; if (x < NB) off[x] += c[u]; }
-    }
+    for (int x = threadIdx.x; x < NB; x += blockDim.x) off[x] += mrow[x];
     __syncthreads();
-    const int lo = (int)min((int64_t)blockIdx.x * a.slab, a.C), hi = (int)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
-    const uint32_t *__restrict__ dr = a.dr;
-    const int32_t *__restrict__ pc = a.perm_cur;
-    for (int s0 = lo; s0 < hi; s0 += PRE * 256) {
-        uint32_t v[PRE];
-        int32_t id[PRE];
+    for (int s0 = lo; s0 < hi; s0 += PS * 256) {
+        if (s0 > lo) {   // slabs larger than one register batch
 #pragma unroll
-        for (int u = 0; u < PRE; ++u) {
-            const int sl = s0 + u * 256 + threadIdx.x;
-            v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
-            id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
+            for (int u = 0; u < PS; ++u) {
+                const int sl = s0 + u * 256 + threadIdx.x;
+                v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
+                id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
+            }
         }
 #pragma unroll
-        for (int u = 0; u < PRE; ++u) {
+        for (int u = 0; u < PS; ++u) {
             const int sl = s0 + u * 256 + threadIdx.x;
             if (sl < hi) {
                 const int db = (int)(v[u] & 0xffffu);
@@ -564,7 +572,7 @@ int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaSt
     return 1;
 }
 
-static size_t scan_smem(int NB) { return ((size_t)NB + 40) * sizeof(uint32_t); }
+static size_t scan_smem(int NB) { return ((size_t)2 * NB + 40) * sizeof(uint32_t); }
 
 int launch_bucket_scatter(const ScatterArgs &a, int G, cudaStream_t st)
 {

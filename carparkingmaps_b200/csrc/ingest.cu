@@ -1,0 +1,61 @@
+// ingest.cu -- createdatamatrix on the device: the Uber Movement rows
+// (sourceid, dstid, hod, mean_travel_time, standard_deviation_travel_time) are scattered into the dense
+// datamatrix[N,N,T,2] the tables are built from.  Reference: src/createdatamatrix.jl:8-23 -- zone ID 0 becomes N,
+// hour 0 becomes 24 (= T), rows are applied in file order, so for duplicate (src,dst,hod) keys the LAST row wins.
+// Uploading the rows instead of the dense array moves 28 B per row instead of 16 B per (i,j,t) cell: ~9x less PCIe
+// traffic for Melbourne-like data (91 % empty, README.md:310).
+//
+// "Last row wins" without a sort: pass 1 claims every touched cell with atomicMax(row index + 1) on the cell's mean
+// slot (row indices are tiny integers = denormal bit patterns, which no travel time has), pass 2 lets the winning
+// row write the std slot, pass 3 the mean slot.  Out-of-range rows are counted and skipped (the reference raises
+// BoundsError).
+#include "kernels.h"
+
+namespace cpm {
+
+__device__ __forceinline__ int64_t row_cell(const int32_t *src, const int32_t *dst, const int32_t *hod, int64_t r, int64_t N, int64_t T)
+{
+    int64_t i = src[r], j = dst[r], h = hod[r];
+    if (i == 0) i = N;        // src/createdatamatrix.jl:9-11
+    if (j == 0) j = N;        // :12-14
+    if (h == 0) h = 24;       // :15-17 (hard-coded 24 in the reference)
+    if (i < 1 || i > N || j < 1 || j > N || h < 1 || h > T) return -1;
+    return (i - 1) + N * ((j - 1) + N * (h - 1));
+}
+
+__global__ void k_rows_claim(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, const int32_t *__restrict__ hod,
+                             int64_t n_rows, int64_t N, int64_t T, double *__restrict__ dm, unsigned long long *__restrict__ n_bad)
+{
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = row_cell(src, dst, hod, r, N, T);
+        if (c < 0) { atomicAdd(n_bad, 1ull); continue; }
+        atomicMax(reinterpret_cast<unsigned long long *>(dm) + c, (unsigned long long)(r + 1));
+    }
+}
+
+template <int SLOT>   // 1: std slab, 0: mean slab (must run last: it overwrites the claim)
+__global__ void k_rows_write(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, const int32_t *__restrict__ hod,
+                             const double *__restrict__ val, int64_t n_rows, int64_t N, int64_t T, double *__restrict__ dm)
+{
+    const int64_t slab = N * N * T;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = row_cell(src, dst, hod, r, N, T);
+        if (c < 0) continue;
+        if (reinterpret_cast<const unsigned long long *>(dm)[c] == (unsigned long long)(r + 1)) dm[c + SLOT * slab] = val[r];
+    }
+}
+
+int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, const double *sd,
+                        int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st)
+{
+    cudaMemsetAsync(dm, 0, (size_t)N * N * T * 2 * sizeof(double), st);   // zeros(number_zones, number_zones, T, 2), :7
+    cudaMemsetAsync(n_bad, 0, sizeof(unsigned long long), st);
+    if (n_rows <= 0) return 0;
+    const int g = sampler_grid(n_rows);
+    k_rows_claim<<<g, 256, 0, st>>>(src, dst, hod, n_rows, N, T, dm, n_bad);
+    k_rows_write<1><<<g, 256, 0, st>>>(src, dst, hod, sd, n_rows, N, T, dm);
+    k_rows_write<0><<<g, 256, 0, st>>>(src, dst, hod, mean, n_rows, N, T, dm);
+    return 3;
+}
+
+}  // namespace cpm

@@ -108,6 +108,10 @@ int launch_normalise_counts(const uint32_t *parking, const uint32_t *driving, in
                             double *parking_out, double *driving_out, double *traffic_out,
                             unsigned long long *traffic_counts_out, cudaStream_t st);
 
+// ---- ingest.cu --------------------------------------------------------------------------------
+int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, const double *sd,
+                        int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st);
+
 // ---- synth.cu ---------------------------------------------------------------------------------
 int launch_synth_city(double *dm, double *dist, int64_t N, int64_t T, uint64_t seed, double density,
                       cudaStream_t st);

@@ -113,6 +113,18 @@ class City:
         L.check(L.lib().cpm_city_upload(self._h, _ptr(dm), _ptr(dist)))
         return self
 
+    def upload_rows(self, sourceid, dstid, hod, mean, stddev, distance_matrix_km):
+        """createdatamatrix on the device (src/createdatamatrix.jl:8-23) from the CSV columns; returns #skipped rows."""
+        cols = [np.ascontiguousarray(a, dtype=np.int32) for a in (sourceid, dstid, hod)]
+        vals = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, stddev)]
+        n = cols[0].shape[0]
+        assert all(a.shape == (n,) for a in cols + vals)
+        dist = _f64F(distance_matrix_km, (self.N, self.N))
+        skipped = C.c_int64()
+        L.check(L.lib().cpm_city_upload_rows(self._h, _ptr(cols[0]), _ptr(cols[1]), _ptr(cols[2]), _ptr(vals[0]), _ptr(vals[1]),
+                                             n, _ptr(dist), C.byref(skipped)))
+        return skipped.value
+
     def synth(self, seed: int, density: float = 1.0):
         L.check(L.lib().cpm_city_synth(self._h, seed, float(density)))
         return self

@@ -145,6 +145,12 @@ int32_t cpm_city_create(cpm_ctx *ctx, int64_t N, int64_t T, cpm_city **out);
 int32_t cpm_city_destroy(cpm_city *city);
 /* inputs: either copied from host, or generated on the device (SURVEY 8d synthetic city) */
 int32_t cpm_city_upload(cpm_city *city, const double *datamatrix, const double *distance_matrix_km);
+/* createdatamatrix on the device -- src/createdatamatrix.jl:8-23: the CSV rows (sourceid, dstid, hod, mean, std) are
+ * scattered into the dense datamatrix; ID 0 -> N, hour 0 -> 24, later rows overwrite earlier ones; rows outside
+ * the matrix are skipped and counted in n_skipped (nullable; the reference raises BoundsError). */
+int32_t cpm_city_upload_rows(cpm_city *city, const int32_t *sourceid, const int32_t *dstid, const int32_t *hod,
+                             const double *mean, const double *stddev, int64_t n_rows,
+                             const double *distance_matrix_km, int64_t *n_skipped);
 int32_t cpm_city_synth(cpm_city *city, uint64_t seed, double density);
 int32_t cpm_city_download_inputs(cpm_city *city, double *datamatrix, double *distance_matrix_km);
 /* tables: built on the device from the inputs (createpdrive / createpdestin) ... */

@@ -164,6 +164,28 @@ static double jl_min(const double *x, i64 n)
 #define DM(i, j, t, k) dm[(i) + N * ((j) + N * ((t) + T * (k)))]
 
 /* ------------------------------------------------------------------------------------ */
+/* createdatamatrix (the scatter, not the CSV parsing) -- src/createdatamatrix.jl:7-23   */
+/* rows applied in order: later rows overwrite earlier ones.  Returns #rows outside the   */
+/* matrix (the reference raises BoundsError there; they are skipped here).               */
+/* ------------------------------------------------------------------------------------ */
+i64 orc_createdatamatrix(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean,
+                         const double *sd, i64 n_rows, i64 N, i64 T, double *dm)
+{
+    i64 bad = 0;
+    memset(dm, 0, (size_t)(N * N * T * 2) * sizeof(double));               /* :7 */
+    for (i64 r = 0; r < n_rows; ++r) {                                     /* :8 */
+        i64 i = src[r], j = dst[r], h = hod[r];
+        if (i == 0) i = N;                                                 /* :9-11 */
+        if (j == 0) j = N;                                                 /* :12-14 */
+        if (h == 0) h = 24;                                                /* :15-17 */
+        if (i < 1 || i > N || j < 1 || j > N || h < 1 || h > T) { ++bad; continue; }
+        DM(i - 1, j - 1, h - 1, 0) = mean[r];                              /* :21 */
+        DM(i - 1, j - 1, h - 1, 1) = sd[r];                                /* :22 */
+    }
+    return bad;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* createpdrive -- src/createpdrive.jl:3-38                                             */
 /* ------------------------------------------------------------------------------------ */
 void orc_createpdrive(const double *dm, const double *dist, i64 N, i64 T,

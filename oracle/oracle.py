@@ -65,6 +65,8 @@ def lib():
                                      C.c_int, ip, ip, dp]
         L.orc_day_counts.restype = i64
         L.orc_rng_init.argtypes = [C.POINTER(_Rng)]
+        L.orc_createdatamatrix.argtypes = [ip, ip, ip, dp, dp, i64, i64, i64, dp]
+        L.orc_createdatamatrix.restype = i64
         _lib = L
     return _lib
 
@@ -113,6 +115,16 @@ class Rng:
 
     def as_injected(self):
         return Rng(mode="injected", u_drive=self.u_drive, u_dest=self.u_dest, u_time=self.u_time, u_dist=self.u_dist)
+
+
+def createdatamatrix(sourceid, dstid, hod, mean, stddev, number_zones, *, T):
+    """The scatter of src/createdatamatrix.jl:7-23 from the CSV columns -> (datamatrix[N,N,T,2], #skipped rows)."""
+    N = int(number_zones)
+    cols = [np.ascontiguousarray(a, dtype=np.int32) for a in (sourceid, dstid, hod)]
+    vals = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, stddev)]
+    dm = np.zeros((N, N, T, 2), order="F")
+    bad = lib().orc_createdatamatrix(_p(cols[0]), _p(cols[1]), _p(cols[2]), _p(vals[0]), _p(vals[1]), cols[0].shape[0], N, T, _p(dm))
+    return dm, bad
 
 
 def createpdrive(datamatrix, distance_matrix_km, number_zones, *, T, p_min, p_max, e_drive):

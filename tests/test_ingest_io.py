@@ -1,0 +1,94 @@
+"""createdatamatrix (row scatter) and the result writers: oracle / host logic on CPU, device scatter on GPU."""
+import numpy as np
+import pytest
+
+from carparkingmaps_b200 import results_io
+from carparkingmaps_b200.synth import synth_city
+from oracle import oracle as O
+
+T = 24
+
+
+def _rows_from_dense(dm, rs, shuffle=True, dup=0):
+    """CSV-style columns of the non-empty cells: zone N is written as ID 0 and hour 24 as 0, as in the Uber files
+    (src/createdatamatrix.jl:9-17 maps them back)."""
+    N = dm.shape[0]
+    i, j, t = np.nonzero(dm[:, :, :, 0])
+    order = rs.permutation(len(i)) if shuffle else np.arange(len(i))
+    i, j, t = i[order], j[order], t[order]
+    src = (i + 1) % N
+    dst = (j + 1) % N
+    hod = (t + 1) % 24
+    mean, sd = dm[i, j, t, 0].copy(), dm[i, j, t, 1].copy()
+    if dup:   # duplicate keys with other values EARLIER in the file: the last row must win
+        k = rs.choice(len(i), dup, replace=False)
+        src = np.concatenate([src[k], src]); dst = np.concatenate([dst[k], dst]); hod = np.concatenate([hod[k], hod])
+        mean = np.concatenate([mean[k] + 1000.0, mean]); sd = np.concatenate([sd[k] + 7.0, sd])
+    return src, dst, hod, mean, sd
+
+
+def test_oracle_createdatamatrix_semantics():
+    rs = np.random.default_rng(0)
+    N = 9
+    dm, _ = synth_city(N, T, seed=2, density=0.3)
+    src, dst, hod, mean, sd = _rows_from_dense(dm, rs, dup=20)
+    got, bad = O.createdatamatrix(src, dst, hod, mean, sd, N, T=T)
+    assert bad == 0
+    np.testing.assert_array_equal(got, dm)                     # ID 0 -> N, hour 0 -> 24, last row wins
+    # literal loop restatement (src/createdatamatrix.jl:8-23)
+    ref = np.zeros_like(dm)
+    for r in range(len(src)):
+        a, b, h = int(src[r]) or N, int(dst[r]) or N, int(hod[r]) or 24
+        ref[a - 1, b - 1, h - 1, 0] = mean[r]; ref[a - 1, b - 1, h - 1, 1] = sd[r]
+    np.testing.assert_array_equal(got, ref)
+    _, bad = O.createdatamatrix([N + 1, 1], [1, 1], [1, 25], [5.0, 6.0], [1.0, 1.0], N, T=T)
+    assert bad == 2                                            # out of range: BoundsError in the reference, skipped here
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,density,dup", [(9, 0.3, 20), (64, 0.09, 500), (40, 1.0, 0)])
+def test_device_row_scatter_matches_oracle(ctx, N, density, dup):
+    from carparkingmaps_b200 import City
+    rs = np.random.default_rng(N)
+    dm, dist = synth_city(N, T, seed=N, density=density)
+    src, dst, hod, mean, sd = _rows_from_dense(dm, rs, dup=dup)
+    src = np.concatenate([src, [N + 5]]); dst = np.concatenate([dst, [1]]); hod = np.concatenate([hod, [3]])
+    mean = np.concatenate([mean, [1.0]]); sd = np.concatenate([sd, [1.0]])
+    city = City(ctx, N, T)
+    skipped = city.upload_rows(src, dst, hod, mean, sd, dist)
+    want, bad = O.createdatamatrix(src, dst, hod, mean, sd, N, T=T)
+    assert skipped == bad == 1
+    dm_d, dist_d = city.download_inputs()
+    np.testing.assert_array_equal(dm_d, want)
+    np.testing.assert_array_equal(dm_d, dm)
+    np.testing.assert_array_equal(dist_d, dist)
+    city.close()
+
+
+def test_julia_float_formatting():
+    cases = {1.0: "1.0", 0.5: "0.5", 1e-5: "1.0e-5", 1.5e-7: "1.5e-7", 0.0001: "0.0001", 123456.789: "123456.789",
+             1e21: "1.0e21", 2.5e22: "2.5e22", 0.0: "0.0", -3.25e-9: "-3.25e-9", float("nan"): "NaN", 0.00012: "0.00012",
+             0.00004166666666666667: "4.1666666666666665e-5" if repr(0.00004166666666666667) == "4.1666666666666665e-05" else None}
+    for x, want in cases.items():
+        if want is not None:
+            assert results_io.jl_float(x) == want, (x, results_io.jl_float(x), want)
+    for x in np.random.default_rng(1).random(200) * 10.0 ** np.random.default_rng(2).integers(-8, 6, 200):
+        assert float(results_io.jl_float(x)) == x             # round-trips
+
+
+def test_result_files_have_the_reference_format(tmp_path):
+    N = 5
+    rs = np.random.default_rng(3)
+    parking = rs.random((N, T)) / N
+    traffic = rs.random(T)
+    path = results_io.createresultsdirectory(str(tmp_path), "Melbourne")
+    results_io.createresultsdirectory(str(tmp_path), "Melbourne")          # tolerates an existing folder (:8-13)
+    results_io.saveresults(path, "melbourne-2017-1-OnlyWeekdays.csv", parking, traffic)
+    results_io.saveparameters(path, 24, N, 1000, N * 1000, 0.5, 0.1, 0.9, 2, 0.0712)
+    lines = open(tmp_path / "Melbourne" / "results_parkingdensities_melbourne-2017-1-OnlyWeekdays.csv").read().splitlines()
+    assert lines[0].split(",") == [f"t = {t}h" for t in range(1, 25)] and len(lines) == N + 1    # src/saveresults.jl:35-38
+    np.testing.assert_array_equal(np.array([[float(v) for v in l.split(",")] for l in lines[1:]]), parking)
+    lines = open(tmp_path / "Melbourne" / "results_trafficactivity_melbourne-2017-1-OnlyWeekdays.csv").read().splitlines()
+    assert len(lines) == 2 and [float(v) for v in lines[1].split(",")] == list(traffic)
+    lines = open(tmp_path / "Melbourne" / "sampling_parameters.csv").read().splitlines()
+    assert lines[0].split(",") == results_io.PARAMETER_HEADER and lines[1].startswith("24.0,5.0,1000.0,5000.0,0.5,0.1,0.9,2.0,0.0712")
