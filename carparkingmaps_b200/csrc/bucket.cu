@@ -499,9 +499,15 @@ __global__ void k_bucket_export_counts(const uint32_t *__restrict__ cnt, const u
     }
 }
 
-__global__ void k_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out)
+// canonical form (whole seconds, fraction < 1 s in 2^-32 units), then ONE conversion to fp64: the same value for any
+// decomposition of the work into CTAs, samplers or GPUs
+__global__ void k_finalize_time(unsigned long long *hi, unsigned long long *lo, double *out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = (double)(*hi) + (double)(*lo) * (1.0 / 4294967296.0);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const unsigned long long h = *hi + (*lo >> 32), l = *lo & 0xffffffffull;
+        *hi = h; *lo = l;
+        *out = (double)h + (double)l * (1.0 / 4294967296.0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -603,7 +609,7 @@ int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N,
     return 1;
 }
 
-int launch_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out, cudaStream_t st)
+int launch_finalize_time(unsigned long long *hi, unsigned long long *lo, double *out, cudaStream_t st)
 {
     k_finalize_time<<<1, 32, 0, st>>>(hi, lo, out);
     return 1;

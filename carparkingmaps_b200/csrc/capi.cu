@@ -718,6 +718,18 @@ extern "C" int32_t cpm_fleet_get_counts(cpm_fleet *f, int64_t *parking, int64_t 
     if (n_lost) *n_lost = (int64_t)sc.lost;
     return CPM_OK;
 }
+extern "C" int32_t cpm_fleet_get_time_fixed(cpm_fleet *f, int64_t *seconds, int64_t *frac32)
+{
+    ARG(f && seconds && frac32);
+    TRY(use(f->ctx));
+    if (f->counts_steps == 0) return fail(CPM_ERR_STATE, "no day has been run on this fleet");
+    Scalars sc;
+    CU(cudaMemcpyAsync(&sc, f->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, f->ctx->st));
+    CU(cudaStreamSynchronize(f->ctx->st));
+    *seconds = (int64_t)sc.t_hi;
+    *frac32 = (int64_t)sc.t_lo;
+    return CPM_OK;
+}
 extern "C" int32_t cpm_fleet_counts_device(cpm_fleet *f, void **dev_ptr, int64_t *n_elems)
 {
     ARG(f && dev_ptr && n_elems);

@@ -91,7 +91,7 @@ int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uin
                      int32_t *perm, cudaStream_t st);
 int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
                                 uint32_t *driving, cudaStream_t st);
-int launch_finalize_time(const unsigned long long *hi, const unsigned long long *lo, double *out, cudaStream_t st);
+int launch_finalize_time(unsigned long long *hi, unsigned long long *lo, double *out, cudaStream_t st);
 
 // helpers
 int launch_fleet_init(int32_t *zone, int64_t C, int64_t cars_per_zone, int64_t car_offset, cudaStream_t st);

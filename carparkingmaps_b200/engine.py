@@ -215,6 +215,12 @@ class Fleet:
         L.check(L.lib().cpm_fleet_get_counts(self._h, _ptr(parking), _ptr(driving), C.byref(ts), C.byref(lost)))
         return parking, driving, ts.value, lost.value
 
+    def time_fixed(self):
+        """(whole seconds, 2^-32 s units) of the last day's driving-time sum: exact integers."""
+        s, f = C.c_int64(), C.c_int64()
+        L.check(L.lib().cpm_fleet_get_time_fixed(self._h, C.byref(s), C.byref(f)))
+        return s.value, f.value
+
     def counts_device(self):
         """(device pointer, n_elems) of the uint32 [2][N,n_steps] count block, for an NCCL all-reduce."""
         p, n = C.c_void_p(), C.c_int64()

@@ -112,13 +112,18 @@ def run_split_city(city, C_total: int, cars_per_zone: int, n_steps: int, *, seed
                   rng=Rng(mode="philox", seed=seed, stream=stream, car_offset=begin))
     counts = fleet_counts_tensor(fleet)
     city.ctx.sync()
-    allreduce_counts(counts)
+    if world > 1:
+        allreduce_counts(counts)
     torch.cuda.synchronize()
-    parking, driving, ts, lost = fleet.counts()          # reads the (now global) device block
-    scal = torch.tensor([ts, float(lost)], dtype=torch.float64, device=counts.device)
-    allreduce_counts(scal)
+    parking, driving, _, lost = fleet.counts()           # reads the (now global) device block
+    sec, frac = fleet.time_fixed()
+    scal = torch.tensor([sec, frac, lost], dtype=torch.int64, device=counts.device)
+    if world > 1:
+        allreduce_counts(scal)                            # integers: exact, order-independent
+    sec, frac, lost = (int(v) for v in scal.tolist())
+    sec, frac = sec + (frac >> 32), frac & 0xffffffff     # canonical form, then one conversion (as the device does)
     fleet.close()
-    return parking, driving, float(scal[0]), int(scal[1])
+    return parking, driving, float(sec) + float(frac) * 2.0 ** -32, lost
 
 
 def run_cities(ctx, cities, *, cars_per_zone=1000, T=24, params=None, density=1.0, rank=0, world=1, seed=0):
@@ -135,7 +140,7 @@ def run_cities(ctx, cities, *, cars_per_zone=1000, T=24, params=None, density=1.
         parking, traffic, A, lost = sample_dataset(city, fleet, cars_per_zone=cars_per_zone, seed=seed + k, **params)
         out.append((k, parking, traffic, A, lost))
         city.close(); fleet.close()
-    merged = [x for part in gather_objects(out) for x in part]
+    merged = [x for part in (gather_objects(out) if world > 1 else [out]) for x in part]
     return sorted(merged, key=lambda x: x[0])
 
 
@@ -149,7 +154,7 @@ def run_sweep(city, initial_zones, params, *, seed=0, rank=0, world=1, want_park
     mine = shards[rank]
     # the Philox stream of a set is its GLOBAL index, so results do not depend on the sharding
     res = sweep(city, initial_zones, params[mine], seed=seed, want_parking=want_parking, streams=2 + mine) if len(mine) else None
-    parts = gather_objects((mine, res))
+    parts = gather_objects((mine, res)) if world > 1 else [(mine, res)]
     tc = np.zeros((city.T, P), dtype=np.int64, order="F")
     A = np.zeros(P)
     pk = np.zeros((city.N, city.T, P), order="F") if want_parking else None

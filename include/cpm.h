@@ -189,6 +189,9 @@ int32_t cpm_run_day(cpm_city *city, cpm_fleet *fleet, const cpm_day_opts *opts);
  * These are raw per-rank counts: a multi-GPU host all-reduces them (SUM) before normalising. */
 int32_t cpm_fleet_get_counts(cpm_fleet *fleet, int64_t *parking, int64_t *driving,
                              double *time_sum, int64_t *n_lost);
+/* the driving-time sum of the last cpm_run_day in fixed point: whole seconds and 2^-32 s units (exact integers, so a
+ * multi-GPU host adds them with an integer all-reduce and gets the unsplit run's value bit for bit) */
+int32_t cpm_fleet_get_time_fixed(cpm_fleet *fleet, int64_t *seconds, int64_t *frac32);
 /* device pointer to the uint32 [2][N,n_steps] count block (parking then driving), for an
  * in-place NCCL all-reduce by the host when one city's cars are split over GPUs */
 int32_t cpm_fleet_counts_device(cpm_fleet *fleet, void **dev_ptr, int64_t *n_elems);

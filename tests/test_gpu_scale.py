@@ -82,3 +82,21 @@ def test_large_n_kernel_shape_matches_gather(ctx, N, cpz):
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
     assert np.array_equal(a[4], b[4]) and (a[0].sum(axis=0) + 0 == C).all()
     city.close()
+
+
+def test_cfg5_table_shape_small_fleet(ctx):
+    """BASELINE.json configs[4] table size (10,000 zones: 80 KB CDF rows, one 512-thread CTA per SM) with a small
+    fleet and two steps per table hour; bucket == gather, cars conserved."""
+    N, cpz, sph = 10000, 30, 2
+    C = N * cpz
+    city = City(ctx, N, T).synth(seed=1, density=0.05).build_pdrive(0.1, 0.9, 0.5).build_pdestin(2, keep_p_dest=False)
+    a = _day(ctx, city, C, cpz, SAMPLER_BUCKET, n_steps=8 * sph)
+    f = Fleet(ctx, C).init(cpz)
+    f.run_day(city, 8 * sph, with_time=True, steps_per_hour=sph, sampler=SAMPLER_BUCKET, rng=Rng(seed=1, stream=1))
+    b = f.counts() + (f.zones(),)
+    g = Fleet(ctx, C).init(cpz)
+    g.run_day(city, 8 * sph, with_time=True, steps_per_hour=sph, sampler=SAMPLER_GATHER, rng=Rng(seed=1, stream=1))
+    c = g.counts() + (g.zones(),)
+    assert np.array_equal(b[0], c[0]) and np.array_equal(b[1], c[1]) and b[2] == c[2] and np.array_equal(b[4], c[4])
+    assert (b[0].sum(axis=0) == C).all() and a[3] == 0
+    f.close(); g.close(); city.close()
