@@ -333,7 +333,8 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES.get(args.workload),
                          "bytes_per_transition": B, "transitions_per_launch": C_, "avg_launch_ms": avg_launch_ms,
-                         "launches_timed": int(step_launches), "kernel_share_of_step": step_ms / ms},
+                         "launches_timed": int(step_launches),
+                         "kernel_share_of_step": avg_launch_ms * (2 * T - 1) / (ms / args.steps)},
             "result_check": {"A_drive": A_drive, "lost": int(lost), "parking_sum_t1": float(parking[:, 0].sum())},
         }
         if world == 1 and not args.no_cpu_baseline:

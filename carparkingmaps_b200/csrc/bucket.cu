@@ -64,6 +64,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (spin > (1u << 24)) __trap();
 }
 
+// Programmatic dependent launch: the three kernels of a step are launched with programmatic stream serialization, so
+// the next kernel's CTAs are scheduled (and run their shared-memory prologue) while the previous kernel drains;
+// pdl_wait() blocks until the previous kernel has completed and its writes are visible.  Every global access of these
+// kernels comes after pdl_wait().  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // shared-memory layout of k_bucket_sample
 // ------------------------------------------------------------------------------------------------
@@ -130,6 +137,8 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
     for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(hist)[x] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 2) s.misc[tid] = 0u;
     __syncthreads();
+    pdl_trigger();
+    pdl_wait();
 
     uint32_t par = 0u;
     unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
@@ -288,6 +297,8 @@ template <int PER>   // PER >= ceil(G / 32): the stripe of one thread lives in r
 __global__ void __launch_bounds__(1024) k_bucket_colscan(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
 {
     __shared__ uint32_t ps[32][33];
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
     const int per = (G + 31) / 32;
     const int g0 = min(G, part * per), g1 = min(G, g0 + per);
@@ -320,6 +331,8 @@ __global__ void __launch_bounds__(1024) k_bucket_colscan(uint32_t *__restrict__ 
 __global__ void __launch_bounds__(1024) k_bucket_colscan_any(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
 {
     __shared__ uint32_t ps[32][33];
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
     const int per = (G + 31) / 32;
     const int g0 = min(G, part * per), g1 = min(G, g0 + per);
@@ -386,6 +399,8 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const ScatterArgs a)
     extern __shared__ uint32_t sm[];   // off[NB] | mrow[NB] | warp_tot[33]
     const int NB = a.NB;
     uint32_t *off = sm, *mrow = sm + NB, *warp_tot = sm + 2 * NB;
+    pdl_trigger();
+    pdl_wait();
     const uint32_t *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
     const int lo = (int)min((int64_t)blockIdx.x * a.slab, a.C), hi = (int)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
     const uint32_t *__restrict__ dr = a.dr;
@@ -554,6 +569,18 @@ static void ensure_smem(K kernel, size_t bytes, size_t &granted)
     }
 }
 
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
 {
     size_t smem = 0; int ctas = 0;
@@ -561,10 +588,10 @@ int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
     static size_t granted[3] = {0, 0, 0};
     if (shape == 1) {
         ensure_smem(k_bucket_sample<256, 1024>, smem, granted[1]);
-        k_bucket_sample<256, 1024><<<G, 256, smem, st>>>(a);
+        launch_pdl(k_bucket_sample<256, 1024>, G, 256, smem, st, a);
     } else if (shape == 2) {
         ensure_smem(k_bucket_sample<512, 2048>, smem, granted[2]);
-        k_bucket_sample<512, 2048><<<G, 512, smem, st>>>(a);
+        launch_pdl(k_bucket_sample<512, 2048>, G, 512, smem, st, a);
     } else return -1;
     return 1;
 }
@@ -572,9 +599,9 @@ int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
 int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaStream_t st)
 {
     const int per = (G + 31) / 32, blocks = (NB + 31) / 32;
-    if (per <= 20) k_bucket_colscan<20><<<blocks, 1024, 0, st>>>(M, G, NB, cnt_next);
-    else if (per <= 40) k_bucket_colscan<40><<<blocks, 1024, 0, st>>>(M, G, NB, cnt_next);
-    else k_bucket_colscan_any<<<blocks, 1024, 0, st>>>(M, G, NB, cnt_next);
+    if (per <= 20) launch_pdl(k_bucket_colscan<20>, blocks, 1024, 0, st, M, G, NB, cnt_next);
+    else if (per <= 40) launch_pdl(k_bucket_colscan<40>, blocks, 1024, 0, st, M, G, NB, cnt_next);
+    else launch_pdl(k_bucket_colscan_any, blocks, 1024, 0, st, M, G, NB, cnt_next);
     return 1;
 }
 
@@ -584,7 +611,7 @@ int launch_bucket_scatter(const ScatterArgs &a, int G, cudaStream_t st)
 {
     static size_t granted = 48 * 1024;
     ensure_smem(k_bucket_scatter, scan_smem(a.NB), granted);
-    k_bucket_scatter<<<G, 256, scan_smem(a.NB), st>>>(a);
+    launch_pdl(k_bucket_scatter, G, 256, scan_smem(a.NB), st, a);
     return 1;
 }
 

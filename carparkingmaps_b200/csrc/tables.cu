@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_rdist(const double *__restrict__ dist, 
     if (k < n) { const double d = dist[k]; rdist[k] = make_double2(d, 1.0 / d); }
 }
 
-constexpr int kMsUnroll = 8;
+constexpr int kMsUnroll = 16;   // loads in flight per thread: only N*T threads exist, so memory parallelism must come from ILP
 
 __global__ void __launch_bounds__(64) k_pdrive_meansum(const double *__restrict__ dm, const double2 *__restrict__ rdist,
                                                        int64_t N, int64_t T, double *__restrict__ mean_sum)
