@@ -80,7 +80,7 @@ struct SampleSmem {
     uint32_t *hist;       // [N+1]   cars of this CTA per destination bin (never cleared inside a launch)
     uint16_t *srch_idx;   // [CH]    chunk-relative slot of each compacted driver
     uint64_t *bar;
-    uint32_t *misc;       // [0],[1] n_search ping-pong counters
+    uint32_t *misc;       // [0],[1] n_search ping-pong counters, [2] scratch of the zone search
 };
 
 __host__ __device__ inline size_t hist_bytes(int64_t N) { return ((size_t)(N + 1) * 4 + 15) / 16 * 16; }
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 
     if (tid == 0) { mbar_init(&s.bar[0], 1); fence_mbar_init(); }
     for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(hist)[x] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid < 2) s.misc[tid] = 0u;
+    if (tid < 3) s.misc[tid] = 0u;
     __syncthreads();
     pdl_trigger();
     pdl_wait();
@@ -148,16 +148,26 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
     const uint32_t slab_lo = (uint32_t)min((int64_t)blockIdx.x * a.slab, a.C);
     const uint32_t slab_hi = (uint32_t)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
     uint32_t pos = slab_lo;
-    int z = (slab_lo < slab_hi) ? zone_of_slot(a.start, NB, slab_lo) : NB;
+    // pull the slab's car ids towards L2 now (one 128-byte line per thread and trip); they are read chunk by chunk below
+    for (uint32_t x = slab_lo + (uint32_t)tid * 32u; x < slab_hi; x += THREADS * 32u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.perm_cur + x));
+    // the slab's first zone, z = #{b : start[b] <= slab_lo} - 1, by one coalesced pass over the bucket starts (a binary
+    // search would be a chain of ~12 dependent L2 loads at the head of every CTA).  Shared memory is NOT used to stage
+    // the starts: the L1 it would take is worth more to the travel-time gathers of the resampling steps.
+    {
+        unsigned below = 0;
+        for (int x = tid; x < NB; x += THREADS) below += (__ldg(a.start + x) <= slab_lo) ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if (lane == 0 && below) atomicAdd(&s.misc[2], below);
+    }
+    __syncthreads();
+    int z = (slab_lo < slab_hi) ? (int)s.misc[2] - 1 : NB;
 
     while (pos < slab_hi) {
         // zone segment [pos, seg_end) of bin z inside the slab; skip empty zones (usually none)
         uint32_t z_end = __ldg(a.start + z + 1);
-        if (z_end <= pos) {
-            ++z;
-            z_end = __ldg(a.start + z + 1);
-            if (z_end <= pos) { z = zone_of_slot(a.start, NB, pos); z_end = __ldg(a.start + z + 1); }
-        }
+        while (z_end <= pos) z_end = __ldg(a.start + (++z) + 1);   // start[NB] = C > pos: terminates
         const uint32_t seg_end = min(z_end, slab_hi);
         const int bin = z;
         const bool is_zone = bin < Ni;
