@@ -36,7 +36,7 @@ WORKLOADS = {
 PARAMS = dict(e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9)   # main.jl:37-40
 # dram__bytes_read.sum + dram__bytes_write.sum per k_bucket_sample launch, from the committed `ncu --set full` capture
 # (profiles/README.md); None where no capture exists
-NCU_TRAFFIC_BYTES = {"cfg2": None}
+NCU_TRAFFIC_BYTES = {"cfg2": 113.5e6}   # profiles/r1_final_metrics_cfg2.summary.txt: mean over the 47 launches of one dataset pass
 
 
 def measured_peak():
@@ -361,7 +361,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--density", type=float, default=1.0, help="share of (i,j,t) entries with data (0.09 = Melbourne-like)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-cars-per-zone", type=int, default=2, help="car subsample of the CPU baseline")
+    ap.add_argument("--cpu-cars-per-zone", type=int, default=16, help="car subsample of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
