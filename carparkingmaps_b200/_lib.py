@@ -73,6 +73,7 @@ SIGNATURES = {
     "cpm_city_upload_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
     "cpm_city_synth": (_i32, [_vp, _u64, _d]),
     "cpm_city_download_inputs": (_i32, [_vp, _vp, _vp]),
+    "cpm_city_prepare_multi_day": (_i32, [_vp]),
     "cpm_city_build_pdrive": (_i32, [_vp, _d, _d, _d]),
     "cpm_city_build_pdestin": (_i32, [_vp, _d, _i32]),
     "cpm_city_set_pdrive": (_i32, [_vp, _vp]),

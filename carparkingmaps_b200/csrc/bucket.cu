@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
                             if (inj) u3 = a.rng.u_time[id + uoff];
                             else philox_pair(a.rng, id, (uint32_t)a.step, 1u, u3, u4);
                             const int64_t od = (int64_t)bin + N * (int64_t)dbin;
-                            const double mean = __ldg(a.dm + od + NN * a.hour);
-                            double sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
+                            double mean, sd;
+                            if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean = ms.x; sd = ms.y; }
+                            else { mean = __ldg(a.dm + od + NN * a.hour); sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab)); }
                             if (sd == 0.0) sd = 0.1 * mean;
                             fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));
                         }

@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI of libcpm.so (declared in include/cpm.h): contexts, device-resident city /
 // fleet handles, and the host-pointer entry points that replace the reference's Julia functions.
 // No CPU fallback: every computing entry point launches the sm_100a kernels or fails.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -86,7 +87,8 @@ struct cpm_ctx {
 struct cpm_city {
     cpm_ctx *ctx = nullptr;
     int64_t N = 0, T = 0;
-    DevBuf dm, dist, rdist, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
+    DevBuf dm, dist, rdist, msd, mean_sum, p_drive, p_dest, norm, cdf, rowzero;
+    bool have_msd = false;   // (mean, std) pair table of the current inputs
     // CDF row block: N doubles, padded to goff doubles, then the row's guide table (G+1 uint16, padded): ldc doubles
     // in total, a multiple of 16 bytes so that a row block is one TMA bulk copy for any N
     int64_t ldc = 0;
@@ -255,7 +257,7 @@ extern "C" int32_t cpm_city_destroy(cpm_city *c)
     if (!c) return CPM_OK;
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->st);
-    c->dm.release(); c->dist.release(); c->rdist.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
+    c->dm.release(); c->dist.release(); c->rdist.release(); c->msd.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
     c->norm.release(); c->cdf.release(); c->rowzero.release();
     delete c;
     return CPM_OK;
@@ -268,7 +270,7 @@ static int32_t city_alloc_inputs(cpm_city *c)
     TRY(c->dist.ensure(NN * sizeof(double)));
     return CPM_OK;
 }
-static void city_invalidate(cpm_city *c) { c->have_meansum = c->have_pdrive = c->have_cdf = c->have_pdest = false; }
+static void city_invalidate(cpm_city *c) { c->have_meansum = c->have_pdrive = c->have_cdf = c->have_pdest = c->have_msd = false; }
 
 extern "C" int32_t cpm_city_upload(cpm_city *c, const double *datamatrix, const double *distance_matrix_km)
 {
@@ -381,6 +383,18 @@ static int32_t city_build_pdestin_async(cpm_city *c, double e_dest, bool write_p
                                         c->ldc, c->goff, c->G, c->rowzero.as<uint8_t>(), write_p ? 1 : 0, c->ctx->st));
     c->have_cdf = true;
     c->have_pdest = write_p;   // without write_p the buffer holds the unnormalised stage only
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_city_prepare_multi_day(cpm_city *c)
+{
+    ARG(c != nullptr);
+    TRY(use(c->ctx));
+    if (!c->have_inputs) return fail(CPM_ERR_STATE, "the city has no inputs");
+    if (c->have_msd) return CPM_OK;
+    TRY(c->msd.ensure((size_t)c->N * c->N * c->T * 2 * sizeof(double)));
+    LAUNCH(c->ctx, launch_pair_table(c->dm.as<double>(), c->N, c->T, c->msd.as<double>(), c->ctx->st));
+    c->have_msd = true;
     return CPM_OK;
 }
 
@@ -580,6 +594,7 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
     a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
     a.rowzero = city->rowzero.as<uint8_t>();
     a.dm = city->dm.as<double>();
+    a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
     a.dist = city->dist.as<double>();
     a.N = N; a.T_tab = city->T;
     a.zone = f->zone.as<int32_t>();
@@ -633,6 +648,7 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     memset(&a, 0, sizeof a);
     a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
     a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
+    a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
     a.N = N; a.T_tab = city->T; a.C = C; a.slab = slab;
     a.start = start; a.dr = f->dest.as<uint32_t>(); a.M = f->pos.as<uint32_t>();
     a.with_time = o->with_time;
@@ -812,10 +828,17 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
     int32_t rc = cpm_fleet_create(ctx, C, &base);
     if (rc == CPM_OK) rc = cpm_fleet_create(ctx, C, &work);
     if (rc == CPM_OK) rc = cpm_fleet_set_zones(base, initial_zones);
+    if (rc == CPM_OK && P >= 2) rc = cpm_city_prepare_multi_day(city);   // many days on the same inputs
     std::vector<unsigned long long> tc((size_t)T);
     bool have_e_dest = false;
     double cur_e_dest = 0.0;
-    for (int64_t p = 0; rc == CPM_OK && p < P; ++p) {
+    // sets are processed grouped by e_dest (stable), so every distinct e_dest builds its CDF once; results land at the
+    // caller's index p and the Philox stream is tied to p, so the order of evaluation is invisible to the caller
+    std::vector<int64_t> order((size_t)P);
+    for (int64_t k = 0; k < P; ++k) order[(size_t)k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return params[x].e_dest < params[y].e_dest; });
+    for (int64_t q = 0; rc == CPM_OK && q < P; ++q) {
+        const int64_t p = order[(size_t)q];
         const cpm_params &pr = params[p];
         if (!have_e_dest || pr.e_dest != cur_e_dest || !city->have_cdf) {   // CDFs are shared by sets with equal e_dest
             rc = city_build_pdestin_async(city, pr.e_dest, false);

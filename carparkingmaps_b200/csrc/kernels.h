@@ -35,6 +35,7 @@ struct StepArgs {
     int32_t goff, G;         // guide offset inside a row block (in doubles) and guide resolution (0 = no guide)
     const uint8_t *rowzero;  // [T][N]
     const double *dm;        // [N,N,T,2] (with_time only)
+    const double2 *msd;      // nullable: [N,N,T] (mean, std) pairs (multi-day runs)
     const double *dist;      // [N,N]     (with_time only)
     int64_t N, T_tab;
     // fleet
@@ -64,6 +65,7 @@ int launch_reduce_partials(const double *partials, int n, double *out, cudaStrea
 // ---- bucket.cu --------------------------------------------------------------------------------
 struct BucketArgs {
     const double *p_drive; const double *cdf; int64_t ldc; int32_t goff, G; const uint8_t *rowzero; const double *dm;
+    const double2 *msd;        // nullable: (mean, std) pairs
     int64_t N, T_tab;
     const int32_t *perm_cur;   // [C] car ids grouped by zone bin
     const uint32_t *start;     // [N+2] first slot of every bin (bin N = lost cars), start[N+1] = C
@@ -113,6 +115,7 @@ int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *h
                         int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st);
 
 // ---- synth.cu ---------------------------------------------------------------------------------
+int launch_pair_table(const double *dm, int64_t N, int64_t T, double *msd, cudaStream_t st);
 int launch_synth_city(double *dm, double *dist, int64_t N, int64_t T, uint64_t seed, double density,
                       cudaStream_t st);
 

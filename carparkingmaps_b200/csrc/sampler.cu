@@ -64,8 +64,9 @@ __global__ void __launch_bounds__(kStepThreads) k_step_gather(const StepArgs a)
                         if (inj) { u3 = a.rng.u_time[i + uoff]; u4 = a.rng.u_dist[i + uoff]; }
                         else philox_pair(a.rng, i, (uint32_t)a.step, 1u, u3, u4);
                         const int64_t od = (int64_t)(z - 1) + N * (int64_t)(dest - 1);
-                        double mean = __ldg(a.dm + od + NN * a.hour);             // :63
-                        double sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));   // :64
+                        double mean, sd;                                          // :63-64
+                        if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean = ms.x; sd = ms.y; }
+                        else { mean = __ldg(a.dm + od + NN * a.hour); sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab)); }
                         if (sd == 0.0) sd = 0.1 * mean;                           // :65-67
                         tt = truncnormal(mean, sd, u3);                           // :68
                         mean = __ldg(a.dist + od);                                // :72

@@ -71,6 +71,21 @@ __global__ void __launch_bounds__(256) k_synth_city(double *__restrict__ dm, dou
     }
 }
 
+// (mean, std) of every (origin, destination, hour) side by side: one 16-byte gather per sampled trip instead of two
+// 8-byte gathers from slabs 1.1 GB apart.  Worth its 4.4 GB of build traffic only when many days are sampled on the
+// same inputs (the model-selection sweep).
+__global__ void __launch_bounds__(256) k_pair_table(const double *__restrict__ dm, int64_t n, double2 *__restrict__ msd)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) msd[k] = make_double2(__ldg(dm + k), __ldg(dm + k + n));
+}
+int launch_pair_table(const double *dm, int64_t N, int64_t T, double *msd, cudaStream_t st)
+{
+    const int64_t n = N * N * T;
+    k_pair_table<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dm, n, reinterpret_cast<double2 *>(msd));
+    return 1;
+}
+
 int launch_synth_city(double *dm, double *dist, int64_t N, int64_t T, uint64_t seed, double density, cudaStream_t st)
 {
     const int64_t NN = N * N;

@@ -135,6 +135,11 @@ class City:
         L.check(L.lib().cpm_city_download_inputs(self._h, _ptr(dm), _ptr(dist)))
         return dm, dist
 
+    def prepare_multi_day(self):
+        """Build the (mean, std) pair table: halves the travel-time gather traffic of every later resampling day."""
+        L.check(L.lib().cpm_city_prepare_multi_day(self._h))
+        return self
+
     def build_pdrive(self, p_min, p_max, e_drive):
         L.check(L.lib().cpm_city_build_pdrive(self._h, p_min, p_max, float(e_drive)))
         return self

@@ -153,6 +153,9 @@ int32_t cpm_city_upload_rows(cpm_city *city, const int32_t *sourceid, const int3
                              const double *distance_matrix_km, int64_t *n_skipped);
 int32_t cpm_city_synth(cpm_city *city, uint64_t seed, double density);
 int32_t cpm_city_download_inputs(cpm_city *city, double *datamatrix, double *distance_matrix_km);
+/* optional: build the (mean, std) pair table that halves the travel-time gather traffic; pays off when many days are
+ * sampled on the same inputs (cpm_sweep calls it itself) */
+int32_t cpm_city_prepare_multi_day(cpm_city *city);
 /* tables: built on the device from the inputs (createpdrive / createpdestin) ... */
 int32_t cpm_city_build_pdrive(cpm_city *city, double p_min, double p_max, double e_drive);
 int32_t cpm_city_build_pdestin(cpm_city *city, double e_dest, int32_t keep_p_dest);

@@ -1,0 +1,42 @@
+"""cfg4-style measurement (BASELINE.json configs[3]): a model-selection sweep of P parameter sets on a cfg2-size city.
+Prints one JSON line: sets/s and sampled car-transitions/s (one resampling day = C*T transitions per set).
+
+    python profiles/sweep_bench.py [--sets 64] [--zones 2400] [--cpz 1000]
+"""
+import argparse
+import itertools
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from carparkingmaps_b200 import City, Context, Fleet, Rng, sweep  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--sets", type=int, default=64)
+ap.add_argument("--zones", type=int, default=2400)
+ap.add_argument("--cpz", type=int, default=1000)
+args = ap.parse_args()
+N, cpz, T = args.zones, args.cpz, 24
+C = N * cpz
+grid = list(itertools.product(np.linspace(0.3, 2.0, 16), [1.0, 2.0, 0.7148157904492584, 3.0], [0.0, 0.05, 0.1, 0.2], np.linspace(0.4, 1.0, 16)))
+# (e_drive, e_dest, p_min, p_max) rows; subsample P of the 4,096-set grid, grouped by e_dest like the real sweep
+rs = np.random.default_rng(0)
+idx = np.sort(rs.choice(len(grid), args.sets, replace=False))
+params = np.array([grid[k] for k in idx])
+with Context(0) as ctx:
+    city = City(ctx, N, T).synth(seed=0, density=1.0).build_pdrive(0.1, 0.9, 0.5).build_pdestin(2, keep_p_dest=False)
+    f = Fleet(ctx, C).init(cpz).run_day(city, T - 1, with_time=False, rng=Rng(seed=1, stream=0))   # the IVP, solved once
+    init = f.zones()
+    f.close()
+    sweep(city, init, params[:2], seed=3)          # warm-up
+    t0 = time.perf_counter()
+    tc, A, _ = sweep(city, init, params, seed=3)
+    dt = time.perf_counter() - t0
+    city.close()
+print(json.dumps({"workload": f"sweep of {args.sets} parameter sets, {N} zones x {cpz} cars/zone, one resampling day each",
+                  "sets": args.sets, "distinct_e_dest": int(len(np.unique(params[:, 1]))), "seconds": dt, "ms_per_set": 1e3 * dt / args.sets,
+                  "transitions_per_s": args.sets * C * T / dt, "A_drive_min_max": [float(A.min()), float(A.max())]}))
