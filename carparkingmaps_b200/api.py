@@ -160,4 +160,15 @@ def zonehistogram(number_zones, state_matrix, transition_matrix, C_):
     return parking, driving, traffic
 
 
+def distancematrix(centroid_lat, centroid_long):
+    """The distance-matrix block of processgeodata (src/processgeodata.jl:150-166) -> distance_matrix_km[N,N]."""
+    lat = np.ascontiguousarray(centroid_lat, dtype=np.float64).ravel()
+    lon = np.ascontiguousarray(centroid_long, dtype=np.float64).ravel()
+    assert lat.shape == lon.shape
+    N = lat.shape[0]
+    out = np.empty((N, N), order="F")
+    L.check(L.lib().cpm_distance_matrix(context()._h, _ptr(lat), _ptr(lon), N, _ptr(out)))
+    return out
+
+
 verbose = False   # print the reference's progress lines (src/resampling.jl:84, src/solveinitialvalueproblem.jl:54)

@@ -1050,6 +1050,22 @@ extern "C" int32_t cpm_correct_parameters(double p_min_next, double p_max_next, 
     return CPM_OK;
 }
 
+extern "C" int32_t cpm_distance_matrix(cpm_ctx *ctx, const double *centroid_lat, const double *centroid_long, int64_t N,
+                                       double *distance_matrix_km)
+{
+    TRY(use(ctx));
+    ARG(centroid_lat && centroid_long && distance_matrix_km && N >= 1);
+    const size_t n = (size_t)N;
+    TRY(ctx->tmp.ensure((2 * n + n * n) * sizeof(double)));
+    double *d_lat = ctx->tmp.as<double>(), *d_lon = d_lat + n, *d_out = d_lon + n;
+    CU(cudaMemcpyAsync(d_lat, centroid_lat, n * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(d_lon, centroid_long, n * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    LAUNCH(ctx, launch_distance_matrix(d_lat, d_lon, N, d_out, ctx->st));
+    CU(cudaMemcpyAsync(distance_matrix_km, d_out, n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}
+
 extern "C" int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const double *trans, int64_t C, int64_t N, int64_t T,
                                       double *parking, double *driving, double *traffic)
 {

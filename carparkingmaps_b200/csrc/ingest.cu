@@ -58,4 +58,27 @@ int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *h
     return 3;
 }
 
+// Centroid distance matrix -- src/processgeodata.jl:150-166: equirectangular formula with the reference's
+// constants (111.3 km per degree, 0.01745 rad per degree), symmetric, diagonal forced to 1 km.
+__global__ void __launch_bounds__(256) k_distance_matrix(const double *__restrict__ lat, const double *__restrict__ lon, int64_t N,
+                                                         double *__restrict__ out)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * N) return;
+    const int64_t i = idx % N, j = idx / N;
+    double d = 1.0;                                                         // :164-166
+    if (i != j) {
+        const int64_t a = i < j ? i : j, b = i < j ? j : i;                 // the reference evaluates the pair with i < j (:153-161)
+        const double c = cos((lat[a] + lat[b]) / 2 * 0.01745);
+        const double dl = lon[a] - lon[b], dp = lat[a] - lat[b];
+        d = 111.3 * sqrt(c * c * (dl * dl) + dp * dp);                      // :158
+    }
+    out[idx] = d;
+}
+int launch_distance_matrix(const double *lat, const double *lon, int64_t N, double *out, cudaStream_t st)
+{
+    k_distance_matrix<<<(unsigned)((N * N + 255) / 256), 256, 0, st>>>(lat, lon, N, out);
+    return 1;
+}
+
 }  // namespace cpm

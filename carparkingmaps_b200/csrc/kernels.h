@@ -114,6 +114,8 @@ int launch_normalise_counts(const uint32_t *parking, const uint32_t *driving, in
 int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, const double *sd,
                         int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st);
 
+int launch_distance_matrix(const double *lat, const double *lon, int64_t N, double *out, cudaStream_t st);
+
 // ---- synth.cu ---------------------------------------------------------------------------------
 int launch_pair_table(const double *dm, int64_t N, int64_t T, double *msd, cudaStream_t st);
 int launch_synth_city(double *dm, double *dist, int64_t N, int64_t T, uint64_t seed, double density,

@@ -138,6 +138,11 @@ int32_t cpm_correct_parameters(double p_min_next, double p_max_next, double p_mi
 int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const double *trans, int64_t C,
                            int64_t N, int64_t T, double *parking, double *driving, double *traffic);
 
+/* The distance matrix block of processgeodata -- src/processgeodata.jl:150-166: equirectangular distance between zone
+ * centroids (degrees), symmetric, diagonal 1 km.  distance_matrix_km: [N,N]. */
+int32_t cpm_distance_matrix(cpm_ctx *ctx, const double *centroid_lat, const double *centroid_long, int64_t N,
+                            double *distance_matrix_km);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Engine API: device-resident city tables and fleets                                       */
 /* ---------------------------------------------------------------------------------------- */

@@ -164,6 +164,22 @@ static double jl_min(const double *x, i64 n)
 #define DM(i, j, t, k) dm[(i) + N * ((j) + N * ((t) + T * (k)))]
 
 /* ------------------------------------------------------------------------------------ */
+/* distance matrix from zone centroids -- src/processgeodata.jl:150-166                 */
+/* ------------------------------------------------------------------------------------ */
+void orc_distancematrix(const double *lat, const double *lon, i64 N, double *out)
+{
+    const double c_lat_long = 111.3, conv_deg_rad = 0.01745;                 /* :151-152 */
+    memset(out, 0, (size_t)(N * N) * sizeof(double));
+    for (i64 i = 0; i < N - 1; ++i)                                          /* :154 */
+        for (i64 j = i; j < N; ++j) {                                        /* :157 */
+            double c = cos((lat[i] + lat[j]) / 2 * conv_deg_rad);
+            double d = c_lat_long * sqrt(c * c * ((lon[i] - lon[j]) * (lon[i] - lon[j])) + (lat[i] - lat[j]) * (lat[i] - lat[j]));
+            out[i + N * j] = d; out[j + N * i] = d;                          /* :159-160 */
+        }
+    for (i64 i = 0; i < N; ++i) out[i + N * i] = 1;                          /* :164-166 */
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* createdatamatrix (the scatter, not the CSV parsing) -- src/createdatamatrix.jl:7-23   */
 /* rows applied in order: later rows overwrite earlier ones.  Returns #rows outside the   */
 /* matrix (the reference raises BoundsError there; they are skipped here).               */

@@ -67,6 +67,7 @@ def lib():
         L.orc_rng_init.argtypes = [C.POINTER(_Rng)]
         L.orc_createdatamatrix.argtypes = [ip, ip, ip, dp, dp, i64, i64, i64, dp]
         L.orc_createdatamatrix.restype = i64
+        L.orc_distancematrix.argtypes = [dp, dp, i64, dp]
         _lib = L
     return _lib
 
@@ -115,6 +116,15 @@ class Rng:
 
     def as_injected(self):
         return Rng(mode="injected", u_drive=self.u_drive, u_dest=self.u_dest, u_time=self.u_time, u_dist=self.u_dist)
+
+
+def distancematrix(centroid_lat, centroid_long):
+    """src/processgeodata.jl:150-166 -> distance_matrix_km[N,N]"""
+    lat = np.ascontiguousarray(centroid_lat, dtype=np.float64).ravel()
+    lon = np.ascontiguousarray(centroid_long, dtype=np.float64).ravel()
+    out = np.zeros((lat.shape[0], lat.shape[0]), order="F")
+    lib().orc_distancematrix(_p(lat), _p(lon), lat.shape[0], _p(out))
+    return out
 
 
 def createdatamatrix(sourceid, dstid, hod, mean, stddev, number_zones, *, T):

@@ -92,3 +92,27 @@ def test_result_files_have_the_reference_format(tmp_path):
     assert len(lines) == 2 and [float(v) for v in lines[1].split(",")] == list(traffic)
     lines = open(tmp_path / "Melbourne" / "sampling_parameters.csv").read().splitlines()
     assert lines[0].split(",") == results_io.PARAMETER_HEADER and lines[1].startswith("24.0,5.0,1000.0,5000.0,0.5,0.1,0.9,2.0,0.0712")
+
+
+def test_oracle_distance_matrix_formula():
+    # src/processgeodata.jl:150-166 with Melbourne-like centroids
+    rs = np.random.default_rng(5)
+    lat, lon = -37.8 + 0.3 * rs.random(12), 144.9 + 0.4 * rs.random(12)
+    d = O.distancematrix(lat, lon)
+    assert (np.diag(d) == 1).all() and np.array_equal(d, d.T)
+    i, j = 2, 7
+    want = 111.3 * np.sqrt(np.cos((lat[i] + lat[j]) / 2 * 0.01745) ** 2 * (lon[i] - lon[j]) ** 2 + (lat[i] - lat[j]) ** 2)
+    np.testing.assert_allclose(d[i, j], want, rtol=1e-14)
+    assert 0 < d[i, j] < 60          # a city-sized box
+
+
+@pytest.mark.gpu
+def test_device_distance_matrix_matches_oracle(ctx):
+    from carparkingmaps_b200 import api
+    rs = np.random.default_rng(6)
+    for N in (1, 7, 300):
+        lat, lon = -37.8 + 0.3 * rs.random(N), 144.9 + 0.4 * rs.random(N)
+        got = api.distancematrix(lat, lon)
+        want = O.distancematrix(lat, lon)
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)     # device cos() vs libm: a few ulp
+        assert (np.diag(got) == 1).all() and np.array_equal(got, got.T)
