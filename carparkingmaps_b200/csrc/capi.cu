@@ -80,6 +80,8 @@ struct cpm_ctx {
     // optional timing of the sampling kernel: one event pair per day (consecutive launches of the step kernel)
     bool profiling = false;
     uint64_t prof_tick = 0;
+    cudaStream_t copy_st = nullptr;          // host-input pipeline: uploads overlap the tables and the IVP
+    cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev;      // start0, stop0, start1, stop1, ...
     std::vector<int64_t> ev_launches; // step-kernel launches bracketed by each pair
 };
@@ -107,7 +109,7 @@ struct cpm_fleet {
     bool zone_valid = true, bucket_valid = false;
     int64_t bucket_N = 0;
     int cur = 0;
-    DevBuf perm[2], dest, pos, bcnt, bdrv, cnt_cur, start_tmp, cursor_tmp, items, n_items;
+    DevBuf perm[2], dest, pos, bcnt, bdrv, cnt_cur, start_tmp, cursor_tmp, items, n_items, lost_acc;
 };
 
 struct Scalars {   // device-side scalar block of a fleet
@@ -170,6 +172,7 @@ extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     ctx->traj_state.release(); ctx->traj_trans.release(); ctx->tmp.release(); ctx->partials.release(); ctx->scalars.release();
     for (auto &b : ctx->u) b.release();
+    if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); for (auto e : ctx->ev_copy) if (e) cudaEventDestroy(e); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->st);
     delete ctx;
     return CPM_OK;
@@ -494,7 +497,7 @@ extern "C" int32_t cpm_fleet_destroy(cpm_fleet *f)
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->st);
     DevBuf *bufs[] = { &f->zone, &f->counts, &f->scalars, &f->norm_out, &f->perm[0], &f->perm[1], &f->dest, &f->pos, &f->bcnt,
-                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->items, &f->n_items };
+                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->items, &f->n_items, &f->lost_acc };
     for (DevBuf *b : bufs) b->release();
     delete f;
     return CPM_OK;
@@ -773,16 +776,18 @@ static int32_t normalise_async(cpm_fleet *f, int64_t N, int64_t T, int64_t C_tot
     return CPM_OK;
 }
 
-extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cpm_params *pr, int64_t cars_per_zone,
-                                      uint64_t seed, int32_t sampler, double *parking, double *traffic, double *A_drive,
-                                      int64_t *n_lost)
+// Enqueues main.jl:82-98 for one dataset on the context's stream (no host synchronisation): tables, fleet init, IVP,
+// resampling, normalisation.  `before_resampling` (nullable) is an event the resampling day waits for: the std slab of
+// datamatrix is only read there, so a host upload can still be in flight while the tables and the IVP run.
+static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cpm_params *pr, int64_t cars_per_zone,
+                                      uint64_t seed, int32_t sampler, cudaEvent_t before_resampling)
 {
-    ARG(city && fleet && pr && cars_per_zone >= 1);
     cpm_ctx *ctx = fleet->ctx;
-    TRY(use(ctx));
     const int64_t N = city->N, T = city->T;
     ARG(fleet->C == N * cars_per_zone);
     city->have_meansum = false;   // one dataset pass recomputes everything, like the reference (no cached stages)
+    TRY(fleet->lost_acc.ensure(sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(fleet->lost_acc.p, 0, sizeof(unsigned long long), ctx->st));
     TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive));                 // main.jl:82
     TRY(city_build_pdestin_async(city, pr->e_dest, false));                                 // main.jl:85
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->st));   // main.jl:88
@@ -791,29 +796,83 @@ extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cp
     memset(&o, 0, sizeof o);
     o.steps_per_hour = 1; o.sampler = sampler;
     o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
-    int64_t lost_ivp = 0;
     if (T > 1) {
         o.n_steps = T - 1; o.with_time = 0; o.rng.stream = 0;                               // main.jl:91-92
         TRY(run_day_async(city, fleet, &o, nullptr));
-        if (n_lost) {
-            Scalars sc;
-            CU(cudaMemcpyAsync(&sc, fleet->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
-            CU(cudaStreamSynchronize(ctx->st));
-            lost_ivp = (int64_t)sc.lost;
-        }
+        // lost-car visits of the IVP survive the next day's reset of the scalar block (device-to-device, no host sync)
+        CU(cudaMemcpyAsync(fleet->lost_acc.p, &fleet->scalars.as<Scalars>()->lost, sizeof(unsigned long long),
+                           cudaMemcpyDeviceToDevice, ctx->st));
     }
+    if (before_resampling) CU(cudaStreamWaitEvent(ctx->st, before_resampling, 0));
     o.n_steps = T; o.with_time = 1; o.rng.stream = 1;                                       // main.jl:95
     TRY(run_day_async(city, fleet, &o, nullptr));
     TRY(normalise_async(fleet, N, T, fleet->C));                                            // saveresults.jl:6-28
+    return CPM_OK;
+}
+
+static int32_t sample_dataset_collect(cpm_city *city, cpm_fleet *fleet, double *parking, double *traffic, double *A_drive,
+                                      int64_t *n_lost)
+{
+    cpm_ctx *ctx = fleet->ctx;
+    const int64_t N = city->N, T = city->T;
     const double *d_parking = fleet->norm_out.as<double>();
     Scalars sc;
+    unsigned long long lost_ivp = 0;
     if (parking) CU(cudaMemcpyAsync(parking, d_parking, (size_t)N * T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     if (traffic) CU(cudaMemcpyAsync(traffic, d_parking + (size_t)N * T, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaMemcpyAsync(&sc, fleet->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&lost_ivp, fleet->lost_acc.p, sizeof lost_ivp, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     if (A_drive) *A_drive = sc.time_sum / ((double)fleet->C * (double)T * 60 * 60);         // averagedrivingtime.jl:10
-    if (n_lost) *n_lost = lost_ivp + (int64_t)sc.lost;
+    if (n_lost) *n_lost = (int64_t)lost_ivp + (int64_t)sc.lost;
     return CPM_OK;
+}
+
+extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cpm_params *pr, int64_t cars_per_zone,
+                                      uint64_t seed, int32_t sampler, double *parking, double *traffic, double *A_drive,
+                                      int64_t *n_lost)
+{
+    ARG(city && fleet && pr && cars_per_zone >= 1);
+    TRY(use(fleet->ctx));
+    TRY(sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, nullptr));
+    return sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);
+}
+
+// The same from HOST inputs in one call: the upload runs on a second stream, the mean slab and the distances first; the
+// tables and the IVP start as soon as those have landed, while the std slab (read only by the resampling day's travel
+// times) is still crossing PCIe.  Pinned host memory (cpm_host_alloc) is needed for the copies to overlap.
+extern "C" int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, const double *datamatrix,
+                                           const double *distance_matrix_km, const cpm_params *pr, int64_t cars_per_zone,
+                                           uint64_t seed, int32_t sampler, double *parking, double *traffic,
+                                           double *A_drive, int64_t *n_lost)
+{
+    ARG(city && fleet && datamatrix && distance_matrix_km && pr && cars_per_zone >= 1);
+    cpm_ctx *ctx = fleet->ctx;
+    ARG(city->ctx == ctx);
+    TRY(use(ctx));
+    TRY(city_alloc_inputs(city));
+    if (!ctx->copy_st) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_copy[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_copy[1], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_copy[2], cudaEventDisableTiming));
+    }
+    const size_t slab = (size_t)city->N * city->N * city->T * sizeof(double);
+    // the copy stream must not overwrite inputs that earlier work on the compute stream still reads
+    CU(cudaEventRecord(ctx->ev_copy[2], ctx->st));
+    CU(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_copy[2], 0));
+    CU(cudaMemcpyAsync(city->dist.p, distance_matrix_km, (size_t)city->N * city->N * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_st));
+    CU(cudaMemcpyAsync(city->dm.p, datamatrix, slab, cudaMemcpyHostToDevice, ctx->copy_st));                       // means
+    CU(cudaEventRecord(ctx->ev_copy[0], ctx->copy_st));
+    CU(cudaMemcpyAsync(city->dm.as<char>() + slab, reinterpret_cast<const char *>(datamatrix) + slab, slab,
+                       cudaMemcpyHostToDevice, ctx->copy_st));                                                       // stds
+    CU(cudaEventRecord(ctx->ev_copy[1], ctx->copy_st));
+    city->have_inputs = true;
+    city_invalidate(city);
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[0], 0));
+    int32_t rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, ctx->ev_copy[1]);
+    if (rc != CPM_OK) { cudaStreamSynchronize(ctx->copy_st); cudaStreamSynchronize(ctx->st); return rc; }
+    return sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);   // the caller may reuse its buffers after this
 }
 
 extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params, int64_t P,

@@ -250,6 +250,21 @@ def sample_dataset(city: City, fleet: Fleet, *, e_drive=0.5, e_dest=2, p_min=0.1
     return parking, traffic, A.value, lost.value
 
 
+def sample_dataset_host(city: City, fleet: Fleet, datamatrix, distance_matrix_km, *, e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9,
+                        cars_per_zone=1000, seed=0, sampler=L.SAMPLER_AUTO, want_parking=True):
+    """main.jl:82-98 for one dataset from HOST arrays, the upload pipelined with the computation.
+    Returns (parking[N,T], traffic[T], A_drive, n_lost)."""
+    dm = _f64F(datamatrix, (city.N, city.N, city.T, 2))
+    dist = _f64F(distance_matrix_km, (city.N, city.N))
+    pr = L.CParams(float(e_drive), float(e_dest), float(p_min), float(p_max))
+    parking = np.empty((city.N, city.T), order="F") if want_parking else None
+    traffic = np.empty(city.T)
+    A, lost = C.c_double(), C.c_int64()
+    L.check(L.lib().cpm_sample_dataset_host(city._h, fleet._h, _ptr(dm), _ptr(dist), C.byref(pr), int(cars_per_zone), int(seed),
+                                            sampler, _ptr(parking), _ptr(traffic), C.byref(A), C.byref(lost)))
+    return parking, traffic, A.value, lost.value
+
+
 def sweep(city: City, initial_zones, params, *, seed=0, common_random_numbers=False, want_parking=False, streams=None):
     """Model-selection sweep over P parameter sets (rows of `params`: e_drive, e_dest, p_min, p_max).
     `streams`: Philox stream id per set (default 2 + p; all equal with common_random_numbers).

@@ -166,11 +166,12 @@ function sampledataset(datamatrix::Array{Float64,4}, distance_matrix_km::Array{F
     check(ccall((:cpm_fleet_create, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx(), N * cpz, fleet))
     parking, traffic, A, lost = zeros(N, T), zeros(1, T), Ref{Float64}(0.0), Ref{Int64}(0)
     try
-        check(ccall((:cpm_city_upload, LIBCPM), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), city[], datamatrix, distance_matrix_km))
         pr = CpmParams(Float64(g(:e_drive)), Float64(g(:e_dest)), Float64(g(:p_min)), Float64(g(:p_max)))
-        check(ccall((:cpm_sample_dataset, LIBCPM), Int32,
-                    (Ptr{Cvoid}, Ptr{Cvoid}, Ref{CpmParams}, Int64, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}),
-                    city[], fleet[], Ref(pr), cpz, UInt64(seed), Int32(0), parking, traffic, A, lost))
+        # one call: the upload of datamatrix is pipelined with the tables and the IVP (include/cpm.h)
+        check(ccall((:cpm_sample_dataset_host, LIBCPM), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{CpmParams}, Int64, UInt64, Int32, Ptr{Float64}, Ptr{Float64},
+                     Ref{Float64}, Ref{Int64}),
+                    city[], fleet[], datamatrix, distance_matrix_km, Ref(pr), cpz, UInt64(seed), Int32(0), parking, traffic, A, lost))
     finally
         ccall((:cpm_fleet_destroy, LIBCPM), Int32, (Ptr{Cvoid},), fleet[])
         ccall((:cpm_city_destroy, LIBCPM), Int32, (Ptr{Cvoid},), city[])

@@ -214,6 +214,14 @@ int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cpm_params *p
                            int64_t cars_per_zone, uint64_t seed, int32_t sampler, double *parking,
                            double *traffic, double *A_drive, int64_t *n_lost);
 
+/* The same from HOST inputs (datamatrix [N,N,T,2], distance_matrix_km [N,N]) in one call: the upload is pipelined with
+ * the computation -- the tables and the IVP start when the mean slab has landed, while the std slab (read only by the
+ * resampling day) is still crossing PCIe.  Use pinned host memory (cpm_host_alloc) for the copies to overlap. */
+int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, const double *datamatrix,
+                                const double *distance_matrix_km, const cpm_params *params, int64_t cars_per_zone,
+                                uint64_t seed, int32_t sampler, double *parking, double *traffic, double *A_drive,
+                                int64_t *n_lost);
+
 /* Model-selection sweep (README.md:956-1316, 1435-1681, 1831-2278 as a batched grid): for each of
  * P parameter sets, rebuild the table(s), restart from `initial_zones` and resample one day.
  * streams (nullable, [P]): Philox stream id of each set (default 2 + p); equal ids give common random
