@@ -283,8 +283,16 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
         e2e_rows = None
         if args.density < 0.5 and world == 1:
             ii, jj, tt = np.nonzero(dm_F[:, :, :, 0])
-            cols = [((ii + 1) % N).astype(np.int32), ((jj + 1) % N).astype(np.int32), ((tt + 1) % 24).astype(np.int32)]
-            vals = [np.ascontiguousarray(dm_F[ii, jj, tt, 0]), np.ascontiguousarray(dm_F[ii, jj, tt, 1])]
+            def pinned(src, dtype):   # pinned host columns, like the dense arrays of the other e2e arm
+                buf, hnd = pinned_f64(lib, (src.size * np.dtype(dtype).itemsize + 7) // 8)
+                out = buf.view(dtype)[: src.size]
+                out[:] = src
+                pins.append(hnd)
+                return out
+
+            pins = []
+            cols = [pinned((ii + 1) % N, np.int32), pinned((jj + 1) % N, np.int32), pinned((tt + 1) % 24, np.int32)]
+            vals = [pinned(dm_F[ii, jj, tt, 0], np.float64), pinned(dm_F[ii, jj, tt, 1], np.float64)]
 
             def rows_step():
                 city.upload_rows(cols[0], cols[1], cols[2], vals[0], vals[1], dist_F)
@@ -302,7 +310,9 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             rows_ms = r0.elapsed_time(r1)
             e2e_rows = {"value": trans_per_step * e2e_steps / (rows_ms * 1e-3), "unit": "transitions/s",
                         "h2d_bytes_per_step": int(len(ii) * 28 + n_dist * 8), "rows": int(len(ii)), "ms_per_step": rows_ms / e2e_steps,
-                        "note": "pageable host columns (sourceid, dstid, hod, mean, std) scattered on the device"}
+                        "note": "pinned host columns (sourceid, dstid, hod, mean, std) scattered on the device"}
+            for hnd in pins:
+                lib.cpm_host_free(hnd)
 
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:

@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
                                                    uint8_t *__restrict__ rowzero)
 {
     __shared__ double tile[4][32][33];
-    __shared__ double carry[4][32];
+    __shared__ uint16_t gidx[4][32][34];   // guide cell reached by each running sum: min(G, floor(run * G)); 0 for NaN
+    __shared__ uint16_t gcarry[4][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t i0 = ((int64_t)blockIdx.x * 4 + w) * 32;
     const int64_t t = blockIdx.y;
@@ -241,7 +242,7 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
     double *out = cdf + (t * N + i0) * ldc;
     const int rows = (int)((N - i0 < 32) ? (N - i0) : 32);
     const double Gd = (double)G;
-    carry[w][lane] = 0.0;
+    gcarry[w][lane] = 0;
     __syncwarp();
     for (int64_t j0 = 0; j0 < N; j0 += 32) {
         double v[32];
@@ -261,28 +262,31 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
             }
             run = run + x;                                             // src/resampling.jl:39
             tile[w][jj][lane] = run;
+            // thresholds b/G <= run  <=>  b <= floor(run * G) (exact: G is a power of two); NaN converts to 0
+            gidx[w][jj][lane] = (uint16_t)__double2int_rd(fmin(run * Gd, Gd));
         }
         __syncwarp();
         if (j0 + lane < N) {
             double *orow = out + j0 + lane;
             const uint16_t jme = (uint16_t)(j0 + lane);
             const double *tl = &tile[w][lane][0];
-            const double *tp = (lane > 0) ? &tile[w][lane - 1][0] : &carry[w][0];
+            const uint16_t *gl = &gidx[w][lane][0];
+            const uint16_t *gp = (lane > 0) ? &gidx[w][lane - 1][0] : &gcarry[w][0];
             for (int r = 0; r < rows; ++r, orow += ldc) {
-                const double cur = tl[r], prv = tp[r];
-                *orow = cur;
-                if (G > 0 && cur > prv) {                              // NaN never compares greater
-                    const int b_lo = __double2int_rd(fmin(prv * Gd, Gd)) + 1;
-                    const int b_hi = __double2int_rd(fmin(cur * Gd, Gd));
-                    if (b_hi >= b_lo) {
-                        uint16_t *g = reinterpret_cast<uint16_t *>(orow - (j0 + lane) + goff);
-                        for (int b = b_lo; b <= b_hi; ++b) g[b] = jme;
-                    }
+                *orow = tl[r];
+                // entry j owns the guide cells (floor(prev*G), floor(cur*G)]: none when the sum did not grow or is NaN
+                const int b_hi = gl[r], b_lo = gp[r] + 1;
+                if (G > 0) {   // most entries own 0, 1 or 2 cells: two predicated stores, a loop only for the rest
+                    uint16_t *g = reinterpret_cast<uint16_t *>(orow - (j0 + lane) + goff);
+                    if (b_hi >= b_lo) g[b_lo] = jme;
+                    if (b_hi > b_lo) g[b_lo + 1] = jme;
+                    if (b_hi > b_lo + 1)
+                        for (int b = b_lo + 2; b <= b_hi; ++b) g[b] = jme;
                 }
             }
         }
         __syncwarp();
-        carry[w][lane] = tile[w][31][lane];
+        gcarry[w][lane] = gidx[w][31][lane];
         __syncwarp();
     }
     if (!live) return;
