@@ -36,11 +36,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+// L2 policy "evict first": streamed-once data (the hour's CDF rows, the travel-time gathers) must not push the car
+// arrays (perm, dr, M: ~35 MB, re-read by the next kernel of the step) out of L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
+}
+__device__ __forceinline__ double ldg_stream(const double *p, uint64_t policy)
+{
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
@@ -142,6 +157,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 
     uint32_t par = 0u;
     unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
+    const uint64_t l2_stream = l2_evict_first_policy();
     int pp = 0;   // which n_search counter the current chunk uses
 
     // this CTA's slab of slots
@@ -182,7 +198,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
             if (need_row && first_chunk && tid == 0) {   // the row buffer's last readers passed the barrier that ended phase B
                 fence_proxy_async();
                 mbar_expect_tx(&s.bar[0], row_bytes);
-                tma_bulk_g2s(s.row, cdf_t + (int64_t)bin * a.ldc, row_bytes, &s.bar[0]);
+                tma_bulk_g2s(s.row, cdf_t + (int64_t)bin * a.ldc, row_bytes, &s.bar[0], l2_stream);
             }
             const int32_t *__restrict__ perm = a.perm_cur + lo;
             uint32_t *__restrict__ out = a.dr + lo;
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
                             const int64_t od = (int64_t)bin + N * (int64_t)dbin;
                             double mean, sd;
                             if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean = ms.x; sd = ms.y; }
-                            else { mean = __ldg(a.dm + od + NN * a.hour); sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab)); }
+                            else { mean = ldg_stream(a.dm + od + NN * a.hour, l2_stream); sd = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream); }
                             if (sd == 0.0) sd = 0.1 * mean;
                             fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));
                         }
