@@ -5,6 +5,12 @@
 // half-rate pipe), so every quotient whose divisor is shared by many elements is computed as
 // "reciprocal once + two FMAs" (div_r below), which returns the same correctly rounded quotient.
 #include "kernels.h"
+#include "async.cuh"
+
+#include <cuda.h>   // CUtensorMap and the encoder's enums (types only: the entry point is looked up at run time)
+
+#include <cstdlib>
+#include <type_traits>
 
 namespace cpm {
 
@@ -71,6 +77,122 @@ __global__ void __launch_bounds__(64) k_pdrive_meansum(const double *__restrict_
     mean_sum[idx] = s / (double)cnt;   // 0/0 -> NaN, as in Julia (:20)
 }
 
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar, uint64_t pol)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pdrive_meansum_tma: the same sums as k_pdrive_meansum with the datamatrix stream staged by TMA.
+// k_pdrive_meansum has only N*T threads (one sequential fp64 chain each), so its memory parallelism comes from 16
+// loads in flight per thread and it stops at about half of the HBM roofline.  Here every warp is its own CTA (all
+// N*T/32 resident at once) and owns a 4-stage shared-memory ring of (8 destinations x 32 origins) tiles filled by
+// one cp.async.bulk.tensor each, three tiles ahead of the running sum (zero fill outside N, and a zero mean is
+// "no data", :15).  The (dist, 1/dist) pairs are shared by the 24 hours and hit L2: plain 16-byte loads, fetched one
+// tile ahead into registers.  Needs even N (tensor-map strides are multiples of 16 bytes).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMtTileJ = 8, kMtStages = 4;
+
+// HT = hours per warp (1 or 2).  With HT = 2 a lane carries two independent chains (hours t, t+1 of its origin) that
+// share every (dist, 1/dist) pair: the pair traffic from L2 -- 2/3 of what this kernel moves -- halves.
+template <int HT>
+__global__ void __launch_bounds__(32) k_pdrive_meansum_tma(const __grid_constant__ CUtensorMap tm_dm, const double *__restrict__ dm,
+                                                           const double2 *__restrict__ rdist, int64_t N, int64_t T,
+                                                           double *__restrict__ mean_sum)
+{
+    __shared__ __align__(128) double in[kMtStages][HT][kMtTileJ][32];
+    __shared__ uint64_t bar[kMtStages];
+    const int lane = threadIdx.x;
+    const int ngrp = (int)(T / HT);
+    const int t0 = (blockIdx.x % ngrp) * HT, i0 = (blockIdx.x / ngrp) * 32;   // consecutive CTAs: same origins, consecutive hours
+    const int64_t i = (int64_t)i0 + lane;                                     // (the pairs they share are fetched from HBM once)
+    const bool live = i < N;
+    const int64_t ic = live ? i : N - 1;
+    const double2 *dr = rdist + ic;
+    const int ntiles = (int)((N + kMtTileJ - 1) / kMtTileJ);
+    constexpr uint32_t kTileBytes = HT * kMtTileJ * 32 * 8;
+    const uint64_t pol = l2_evict_first_policy();
+
+    if (elect_one()) {
+#pragma unroll
+        for (int s = 0; s < kMtStages; ++s) mbar_init(&bar[s], 1);
+        fence_mbar_init();
+        for (int k = 0; k < kMtStages - 1 && k < ntiles; ++k) {
+            mbar_expect_tx(&bar[k], kTileBytes);
+            tma_load_3d(&in[k][0][0][0], &tm_dm, i0, k * kMtTileJ, t0, &bar[k], pol);
+        }
+    }
+    __syncwarp();
+
+    double2 dv[kMtTileJ], dn[kMtTileJ];
+    auto fetch_pairs = [&](int k, double2 *dst) {
+        const int64_t j0 = (int64_t)k * kMtTileJ;
+#pragma unroll
+        for (int u = 0; u < kMtTileJ; ++u) dst[u] = (j0 + u < N) ? __ldg(dr + N * (j0 + u)) : make_double2(1.0, 1.0);
+    };
+    fetch_pairs(0, dv);
+    double s[HT];
+    int cnt[HT];
+#pragma unroll
+    for (int h = 0; h < HT; ++h) { s[h] = 0.0; cnt[h] = 0; }
+    for (int k = 0; k < ntiles; ++k) {
+        const int st = k & (kMtStages - 1);
+        if (k + 1 < ntiles) fetch_pairs(k + 1, dn);
+        mbar_wait(&bar[st], (uint32_t)(k / kMtStages) & 1u);
+#pragma unroll
+        for (int u = 0; u < kMtTileJ; ++u) {
+#pragma unroll
+            for (int h = 0; h < HT; ++h) {
+                const double mv = in[st][h][u][lane];
+                if (mv != 0.0) { s[h] = s[h] + div_r(mv, dv[u].x, dv[u].y); ++cnt[h]; }   // :15-17
+            }
+        }
+        __syncwarp();   // every lane has consumed in[st]
+        const int kn = k + kMtStages - 1;
+        if (kn < ntiles && elect_one()) {   // refill the stage consumed in the previous iteration
+            const int sn = kn & (kMtStages - 1);
+            mbar_expect_tx(&bar[sn], kTileBytes);
+            tma_load_3d(&in[sn][0][0][0], &tm_dm, i0, kn * kMtTileJ, t0, &bar[sn], pol);
+        }
+#pragma unroll
+        for (int u = 0; u < kMtTileJ; ++u) dv[u] = dn[u];
+    }
+    if (!live) return;
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+        const int64_t t = t0 + h;
+        double sh = s[h];
+        if (!(fabs(sh) < 1.0e300)) {   // a zero / non-finite distance or an overflow: redo the row with the division instruction
+            const double *m = dm + i + N * N * t;
+            sh = 0.0;
+            for (int64_t j = 0; j < N; ++j) {
+                const double mv = __ldg(m + N * j);
+                if (mv != 0.0) sh = sh + mv / __ldg(dr + N * j).x;
+            }
+        }
+        mean_sum[i + N * t] = sh / (double)cnt[h];   // 0/0 -> NaN, as in Julia (:20)
+    }
+}
+
 // createpdrive, part 2 (:22-34): NaN-propagating max/min over t, then the affine map.  One thread per zone.
 __global__ void k_pdrive_finish(const double *__restrict__ mean_sum, int64_t N, int64_t T, double p_min, double p_max,
                                 double e_drive, double *__restrict__ p_drive)
@@ -101,6 +223,21 @@ int launch_pdrive_meansum(const double *dm, const double *dist, double *rdist, i
     double2 *dr = reinterpret_cast<double2 *>(rdist);   // [N,N] pairs (dist, 1/dist)
     k_rdist<<<(unsigned)((NN + 255) / 256), 256, 0, st>>>(dist, NN, dr);
     (void)n;
+    EncodeTiledFn enc = encode_tiled();
+    if (enc && N % 2 == 0 && N >= 2) {   // dm's mean slab as [t][j][o] fp64, box 32 (o) x 8 (j) x HT hours
+        CUtensorMap tm;
+        const cuuint64_t dim[3] = {(cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)T};
+        const cuuint64_t str[2] = {(cuuint64_t)N * 8, (cuuint64_t)N * N * 8};
+        const cuuint32_t ht = (T % 2 == 0) ? 2 : 1;
+        const cuuint32_t box[3] = {32, (cuuint32_t)kMtTileJ, ht}, ones[3] = {1, 1, 1};
+        if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(dm), dim, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+            const unsigned grid = (unsigned)(((N + 31) / 32) * (T / ht));
+            if (ht == 2) k_pdrive_meansum_tma<2><<<grid, 32, 0, st>>>(tm, dm, dr, N, T, mean_sum);
+            else         k_pdrive_meansum_tma<1><<<grid, 32, 0, st>>>(tm, dm, dr, N, T, mean_sum);
+            return 2;
+        }
+    }
     k_pdrive_meansum<<<(unsigned)(((N + 63) / 64) * T), 64, 0, st>>>(dm, dr, N, T, mean_sum);
     return 2;
 }
@@ -238,6 +375,7 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
     bool div = false;
     if (DIVIDE) { nf = norm[ic + N * t]; div = nf > 0.0; rnf = 1.0 / nf; }   // NaN -> skip (:40)
     const bool fast = recip_ok(rnf);
+    const bool warp_straight = __all_sync(0xffffffffu, fast || !div);
     double run = 0.0;
     double *out = cdf + (t * N + i0) * ldc;
     const int rows = (int)((N - i0 < 32) ? (N - i0) : 32);
@@ -253,35 +391,79 @@ __global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, 
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) v[jj] = (j0 + jj < N) ? p[N * (j0 + jj)] : 0.0;
         }
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
+        // One step of the running sum.  STRAIGHT: every lane of the warp takes the reciprocal path (or does not
+        // divide), so the step is branch-free; otherwise lanes whose reciprocal is unusable call the division.
+        auto step = [&](int jj, auto straight) {
             double x = v[jj];
-            if (DIVIDE && div) {
-                x = fast ? div_r(x, nf, rnf) : div_slow(x, nf);        // :42
-                if (WRITE_P && live && j0 + jj < N) p[N * (j0 + jj)] = x;
+            if (DIVIDE) {
+                if constexpr (decltype(straight)::value) {
+                    const double q = div_r(x, nf, rnf);
+                    x = div ? q : x;                                   // :40-42
+                } else if (div) x = fast ? div_r(x, nf, rnf) : div_slow(x, nf);
+                if (WRITE_P && div && live && j0 + jj < N) p[N * (j0 + jj)] = x;
             }
             run = run + x;                                             // src/resampling.jl:39
             tile[w][jj][lane] = run;
-            // thresholds b/G <= run  <=>  b <= floor(run * G) (exact: G is a power of two); NaN converts to 0
-            gidx[w][jj][lane] = (uint16_t)__double2int_rd(fmin(run * Gd, Gd));
+            // thresholds b/G <= run  <=>  b <= floor(run * G) (exact: G is a power of two).  The conversion saturates
+            // (Inf -> INT_MAX) and maps NaN to 0: a NaN sum owns no cell, the tail fix-up below fills them.
+            gidx[w][jj][lane] = (uint16_t)min(max(__double2int_rd(run * Gd), 0), G);
+        };
+        if (warp_straight) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) step(jj, std::true_type{});
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) step(jj, std::false_type{});   // full unroll: v[] stays in registers
         }
         __syncwarp();
         if (j0 + lane < N) {
-            double *orow = out + j0 + lane;
+            // This loop is 2/3 of the kernel's instructions (profiles/README.md), so it is written for instruction
+            // count: one byte pointer per row (bumped by the row pitch), the guide base at a loop-invariant distance
+            // from it, and a full unroll for complete tiles.
+            char *rowp = reinterpret_cast<char *>(out + j0 + lane);                    // &cdf[row 0][j]
+            const int64_t gdelta = ((int64_t)goff - (j0 + lane)) * 8;                  // &cdf[r][j] -> guide cells of row r
+            const int64_t pitch = ldc * 8;
             const uint16_t jme = (uint16_t)(j0 + lane);
             const double *tl = &tile[w][lane][0];
             const uint16_t *gl = &gidx[w][lane][0];
             const uint16_t *gp = (lane > 0) ? &gidx[w][lane - 1][0] : &gcarry[w][0];
-            for (int r = 0; r < rows; ++r, orow += ldc) {
-                *orow = tl[r];
-                // entry j owns the guide cells (floor(prev*G), floor(cur*G)]: none when the sum did not grow or is NaN
-                const int b_hi = gl[r], b_lo = gp[r] + 1;
-                if (G > 0) {   // most entries own 0, 1 or 2 cells: two predicated stores, a loop only for the rest
-                    uint16_t *g = reinterpret_cast<uint16_t *>(orow - (j0 + lane) + goff);
-                    if (b_hi >= b_lo) g[b_lo] = jme;
-                    if (b_hi > b_lo) g[b_lo + 1] = jme;
-                    if (b_hi > b_lo + 1)
-                        for (int b = b_lo + 2; b <= b_hi; ++b) g[b] = jme;
+            // entry j owns the guide cells (floor(prev*G), floor(cur*G)]: none when the sum did not grow or is NaN.
+            // Nearly all entries own 0-3 cells: three predicated stores in the straight-line body; the few that own
+            // more are finished by a second pass that runs only when the tile has one.
+            int maxown = 0;
+            auto put = [&](int r, auto guide) {
+                *reinterpret_cast<double *>(rowp) = tl[r];
+                if constexpr (decltype(guide)::value) {
+                    const int b_prev = gp[r], own = (int)gl[r] - b_prev;
+                    uint16_t *g = reinterpret_cast<uint16_t *>(rowp + gdelta) + b_prev;
+                    if (own >= 1) g[1] = jme;
+                    if (own >= 2) g[2] = jme;
+                    if (own >= 3) g[3] = jme;
+                    maxown = max(maxown, own);
+                }
+                rowp += pitch;
+            };
+            if (G > 0) {
+                if (rows == 32) {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) put(r, std::true_type{});
+                } else {
+                    for (int r = 0; r < rows; ++r) put(r, std::true_type{});
+                }
+                if (maxown > 3) {
+                    char *gp8 = reinterpret_cast<char *>(out + j0 + lane) + gdelta;
+                    for (int r = 0; r < rows; ++r, gp8 += pitch) {
+                        const int b_prev = gp[r], own = (int)gl[r] - b_prev;
+                        uint16_t *g = reinterpret_cast<uint16_t *>(gp8) + b_prev;
+                        for (int c = 4; c <= own; ++c) g[c] = jme;
+                    }
+                }
+            } else {
+                if (rows == 32) {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) put(r, std::false_type{});
+                } else {
+                    for (int r = 0; r < rows; ++r) put(r, std::false_type{});
                 }
             }
         }
