@@ -263,14 +263,15 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 // k_bucket_colscan: M[g][b] <- sum_{g' < g} M[g'][b] (exclusive, in place); cnt_next[b] <- sum_g M[g][b].
 // One CTA per 32 destination columns: 32 x 32 threads, each sums / rescans a stripe of slabs; coalesced 128 B rows.
 // ------------------------------------------------------------------------------------------------
-template <int PER>   // PER >= ceil(G / 32): the stripe of one thread lives in registers (one pass over M)
-__global__ void __launch_bounds__(1024) k_bucket_colscan(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
+template <int PER, int COLS, int PARTS>   // PER >= ceil(G / PARTS): the stripe of one thread lives in registers (one pass over M)
+__global__ void __launch_bounds__(COLS * PARTS) k_bucket_colscan(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
 {
-    __shared__ uint32_t ps[32][33];
+    __shared__ uint32_t ps[PARTS][COLS + 1];
     pdl_trigger();
     pdl_wait();
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
-    const int per = (G + 31) / 32;
+    const int col = threadIdx.x % COLS, part = threadIdx.x / COLS;
+    const int c = blockIdx.x * COLS + col;
+    const int per = (G + PARTS - 1) / PARTS;
     const int g0 = min(G, part * per), g1 = min(G, g0 + per);
     const bool live = c < NB;
     uint32_t v[PER];
@@ -282,10 +283,10 @@ __global__ void __launch_bounds__(1024) k_bucket_colscan(uint32_t *__restrict__ 
     }
 #pragma unroll
     for (int u = 0; u < PER; ++u) sum += v[u];
-    ps[part][threadIdx.x & 31] = sum;
+    ps[part][col] = sum;
     __syncthreads();
     uint32_t run = 0;
-    for (int p = 0; p < part; ++p) run += ps[p][threadIdx.x & 31];
+    for (int p = 0; p < part; ++p) run += ps[p][col];
     if (live) {
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(1024) k_bucket_colscan(uint32_t *__restrict__ 
             if (g < g1) M[(size_t)g * NB + c] = run;
             run += v[u];
         }
-        if (part == 31) cnt_next[c] = run;   // the last stripe ends with the column total
+        if (part == PARTS - 1) cnt_next[c] = run;   // the last stripe ends with the column total
     }
 }
 
@@ -568,10 +569,11 @@ int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
 
 int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaStream_t st)
 {
-    const int per = (G + 31) / 32, blocks = (NB + 31) / 32;
-    if (per <= 20) launch_pdl(k_bucket_colscan<20>, blocks, 1024, 0, st, M, G, NB, cnt_next);
-    else if (per <= 40) launch_pdl(k_bucket_colscan<40>, blocks, 1024, 0, st, M, G, NB, cnt_next);
-    else launch_pdl(k_bucket_colscan_any, blocks, 1024, 0, st, M, G, NB, cnt_next);
+    // 8 columns x 64 stripes per CTA: ~NB/8 CTAs (two per SM at Melbourne scale) instead of NB/32 on half of the SMs
+    const int per64 = (G + 63) / 64, per32 = (G + 31) / 32;
+    if (per64 <= 10) launch_pdl(k_bucket_colscan<10, 8, 64>, (NB + 7) / 8, 512, 0, st, M, G, NB, cnt_next);
+    else if (per32 <= 40) launch_pdl(k_bucket_colscan<40, 32, 32>, (NB + 31) / 32, 1024, 0, st, M, G, NB, cnt_next);
+    else launch_pdl(k_bucket_colscan_any, (NB + 31) / 32, 1024, 0, st, M, G, NB, cnt_next);
     return 1;
 }
 
