@@ -68,6 +68,7 @@ SIGNATURES = {
     "cpm_correct_parameters": (_i32, [_d, _d, _d, _d, _vp]),
     "cpm_zone_histogram": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "cpm_distance_matrix": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "cpm_polygon_centroids": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "cpm_city_create": (_i32, [_vp, _i64, _i64, _pp]),
     "cpm_city_destroy": (_i32, [_vp]),
     "cpm_city_upload": (_i32, [_vp, _vp, _vp]),

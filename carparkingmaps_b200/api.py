@@ -171,4 +171,16 @@ def distancematrix(centroid_lat, centroid_long):
     return out
 
 
+def polygoncentroids(longitude_matrix, latitude_matrix):
+    """The polygon block of processgeodata (src/processgeodata.jl:99-148): zero-terminated vertex lists [N,V] ->
+    (centroid_lat[N], centroid_long[N], area_polygon[N])."""
+    lon = _chkF(longitude_matrix, np.float64, "longitude_matrix")
+    lat = _chkF(latitude_matrix, np.float64, "latitude_matrix")
+    assert lon.ndim == 2 and lon.shape == lat.shape
+    N, V = lon.shape
+    c_lat, c_lon, area = np.empty(N), np.empty(N), np.empty(N)
+    L.check(L.lib().cpm_polygon_centroids(context()._h, _ptr(lon), _ptr(lat), N, V, _ptr(c_lat), _ptr(c_lon), _ptr(area)))
+    return c_lat, c_lon, area
+
+
 verbose = False   # print the reference's progress lines (src/resampling.jl:84, src/solveinitialvalueproblem.jl:54)

@@ -1125,6 +1125,26 @@ extern "C" int32_t cpm_distance_matrix(cpm_ctx *ctx, const double *centroid_lat,
     return CPM_OK;
 }
 
+extern "C" int32_t cpm_polygon_centroids(cpm_ctx *ctx, const double *longitude_matrix, const double *latitude_matrix, int64_t N,
+                                         int64_t V, double *centroid_lat, double *centroid_long, double *area_polygon)
+{
+    TRY(use(ctx));
+    ARG(longitude_matrix && latitude_matrix && centroid_lat && centroid_long && N >= 1 && V >= 2);
+    // the reference walks at most 10,000 vertices per zone (src/processgeodata.jl:107,132): only those columns travel
+    const int64_t Vd = V < 10001 ? V : 10001;
+    const size_t n = (size_t)N, nv = n * (size_t)Vd;
+    TRY(ctx->tmp.ensure((2 * nv + 3 * n) * sizeof(double)));
+    double *d_lon = ctx->tmp.as<double>(), *d_lat = d_lon + nv, *d_cla = d_lat + nv, *d_clo = d_cla + n, *d_ar = d_clo + n;
+    CU(cudaMemcpyAsync(d_lon, longitude_matrix, nv * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // [N,V] column-major:
+    CU(cudaMemcpyAsync(d_lat, latitude_matrix, nv * sizeof(double), cudaMemcpyHostToDevice, ctx->st));    // the first Vd columns are contiguous
+    LAUNCH(ctx, launch_polygon_centroids(d_lon, d_lat, N, Vd, d_cla, d_clo, d_ar, ctx->st));
+    CU(cudaMemcpyAsync(centroid_lat, d_cla, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(centroid_long, d_clo, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    if (area_polygon) CU(cudaMemcpyAsync(area_polygon, d_ar, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return CPM_OK;
+}
+
 extern "C" int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const double *trans, int64_t C, int64_t N, int64_t T,
                                       double *parking, double *driving, double *traffic)
 {

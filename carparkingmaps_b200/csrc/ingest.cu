@@ -81,4 +81,61 @@ int launch_distance_matrix(const double *lat, const double *lon, int64_t N, doub
     return 1;
 }
 
+// Polygon area and centroid -- src/processgeodata.jl:99-148.  One thread per zone walks its
+// zero-terminated vertex list ([N,V] column-major: the loads of a warp are coalesced across zones) in the reference's
+// order of operations: the area pass stops at the terminator and closes the ring in place, the centroid pass runs
+// over all J columns without stopping at zeros.  lon/lat are the device copies (modified like the reference's).
+__global__ void __launch_bounds__(128) k_polygon_centroids(double *__restrict__ lon, double *__restrict__ lat, int64_t N, int64_t V,
+                                                           double *__restrict__ c_lat, double *__restrict__ c_lon,
+                                                           double *__restrict__ area)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int64_t J = (V - 1 < 10000) ? V - 1 : 10000;
+    double *lo = lon + i, *la = lat + i;   // vertex j (1-based) at [N * (j - 1)]
+    double a = 0.0, cl = 0.0, ca = 0.0;
+    const double lo1 = lo[0], la1 = la[0];
+    if (lo1 != 0.0) {                                                           // :105
+        double s = 0.0;
+        double pl = 0.0, pa = 0.0;                                              // vertex j-1
+        double xl = lo1, xa = la1;                                              // vertex j
+        for (int64_t j = 1; j <= J; ++j) {                                      // :107
+            if (xl == 0.0) {                                                    // :108
+                s = s - (pa * xl - xa * pl);                                    // :110
+                xl = lo1; xa = la1;
+                lo[N * (j - 1)] = xl; la[N * (j - 1)] = xa;                     // :113-114
+                s = s + (pa * xl - xa * pl);                                    // :117
+                break;
+            }
+            const double nl = lo[N * j], na = la[N * j];                        // vertex j+1
+            s = s + (xa * nl - na * xl);                                        // :120
+            pl = xl; pa = xa; xl = nl; xa = na;
+        }
+        a = s / 2;                                                              // :123
+        double sl = 0.0, sa = 0.0;
+        pl = 0.0; pa = 0.0; xl = lo[0]; xa = la[0];
+        for (int64_t j = 1; j <= J; ++j) {                                      // :132 (no break)
+            const double nl = lo[N * j], na = la[N * j];
+            if (xl == 0.0) {
+                const double cr = pl * xa - xl * pa;
+                sl = sl - (pl + xl) * cr;                                       // :135
+                sa = sa - (pa + xa) * cr;                                       // :136
+            } else {
+                const double cr = xl * na - nl * xa;
+                sl = sl + (xl + nl) * cr;                                       // :138
+                sa = sa + (xa + na) * cr;                                       // :139
+            }
+            pl = xl; pa = xa; xl = nl; xa = na;
+        }
+        cl = -sl / (6 * a);                                                     // :142
+        ca = -sa / (6 * a);                                                     // :143
+    }
+    area[i] = a; c_lon[i] = cl; c_lat[i] = ca;
+}
+int launch_polygon_centroids(double *lon, double *lat, int64_t N, int64_t V, double *c_lat, double *c_lon, double *area, cudaStream_t st)
+{
+    k_polygon_centroids<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(lon, lat, N, V, c_lat, c_lon, area);
+    return 1;
+}
+
 }  // namespace cpm

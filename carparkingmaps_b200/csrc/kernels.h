@@ -115,6 +115,7 @@ int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *h
                         int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st);
 
 int launch_distance_matrix(const double *lat, const double *lon, int64_t N, double *out, cudaStream_t st);
+int launch_polygon_centroids(double *lon, double *lat, int64_t N, int64_t V, double *c_lat, double *c_lon, double *area, cudaStream_t st);
 
 // ---- synth.cu ---------------------------------------------------------------------------------
 int launch_pair_table(const double *dm, int64_t N, int64_t T, double *msd, cudaStream_t st);

@@ -143,6 +143,14 @@ int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const double *tra
 int32_t cpm_distance_matrix(cpm_ctx *ctx, const double *centroid_lat, const double *centroid_long, int64_t N,
                             double *distance_matrix_km);
 
+/* The polygon block of processgeodata -- src/processgeodata.jl:99-148: signed area and centroid of every zone from
+ * its zero-terminated vertex list.  longitude_matrix / latitude_matrix: [N,V] column-major as the reference fills them
+ * (:17-18, row = zone, 0 = end of list); at most the first 10,000 vertices of a zone are used, as in the reference.
+ * The inputs are not modified (the reference closes each ring in place; here that happens on the device copy).
+ * centroid_lat / centroid_long / area_polygon: [N]; zones without vertices give 0.  area_polygon may be NULL. */
+int32_t cpm_polygon_centroids(cpm_ctx *ctx, const double *longitude_matrix, const double *latitude_matrix, int64_t N,
+                              int64_t V, double *centroid_lat, double *centroid_long, double *area_polygon);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Engine API: device-resident city tables and fleets                                       */
 /* ---------------------------------------------------------------------------------------- */

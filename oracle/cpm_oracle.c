@@ -180,6 +180,55 @@ void orc_distancematrix(const double *lat, const double *lon, i64 N, double *out
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* polygon area and centroid from zero-terminated vertex lists -- src/processgeodata.jl:99-148 */
+/* lon/lat: [N,V] column-major, row i = the vertices of zone i+1 in file order, 0 = end.       */
+/* Like the reference, the area pass closes the ring in place (writes the first vertex over     */
+/* the terminator, :113-114) and the centroid pass does NOT stop at a zero (:130-141): it runs  */
+/* over all J = min(10000, V-1) columns.  A row without a terminator inside J columns (the       */
+/* reference then indexes out of bounds) leaves the ring open: its sums simply end at J.         */
+/* ------------------------------------------------------------------------------------ */
+void orc_polygoncentroids(double *lon, double *lat, i64 N, i64 V, double *c_lat, double *c_lon, double *area)
+{
+#define LO(i, j) lon[(i) + N * ((j) - 1)]
+#define LA(i, j) lat[(i) + N * ((j) - 1)]
+    const i64 J = (V - 1 < 10000) ? V - 1 : 10000;                            /* j+1 must exist */
+    for (i64 i = 0; i < N; ++i) { c_lat[i] = 0; c_lon[i] = 0; area[i] = 0; }  /* :99-101 */
+    for (i64 i = 0; i < N; ++i) {                                             /* :104 */
+        if (LO(i, 1) == 0) continue;                                          /* :105 */
+        double s = 0;
+        for (i64 j = 1; j <= J; ++j) {                                        /* :107 */
+            if (LO(i, j) == 0) {                                              /* :108 */
+                s = s - (LA(i, j - 1) * LO(i, j) - LA(i, j) * LO(i, j - 1));  /* :110 */
+                LO(i, j) = LO(i, 1); LA(i, j) = LA(i, 1);                     /* :113-114 */
+                s = s + (LA(i, j - 1) * LO(i, j) - LA(i, j) * LO(i, j - 1));  /* :117 */
+                break;
+            }
+            s = s + (LA(i, j) * LO(i, j + 1) - LA(i, j + 1) * LO(i, j));      /* :120 */
+        }
+        area[i] = s / 2;                                                      /* :123 */
+    }
+    for (i64 i = 0; i < N; ++i) {                                             /* :128 */
+        if (LO(i, 1) == 0) continue;
+        double sl = 0, sa = 0;
+        for (i64 j = 1; j <= J; ++j) {                                        /* :132, no break */
+            if (LO(i, j) == 0) {
+                const double cr = LO(i, j - 1) * LA(i, j) - LO(i, j) * LA(i, j - 1);
+                sl = sl - (LO(i, j - 1) + LO(i, j)) * cr;                     /* :135 */
+                sa = sa - (LA(i, j - 1) + LA(i, j)) * cr;                     /* :136 */
+            } else {
+                const double cr = LO(i, j) * LA(i, j + 1) - LO(i, j + 1) * LA(i, j);
+                sl = sl + (LO(i, j) + LO(i, j + 1)) * cr;                     /* :138 */
+                sa = sa + (LA(i, j) + LA(i, j + 1)) * cr;                     /* :139 */
+            }
+        }
+        c_lon[i] = -sl / (6 * area[i]);                                       /* :142 */
+        c_lat[i] = -sa / (6 * area[i]);                                       /* :143 */
+    }
+#undef LO
+#undef LA
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* createdatamatrix (the scatter, not the CSV parsing) -- src/createdatamatrix.jl:7-23   */
 /* rows applied in order: later rows overwrite earlier ones.  Returns #rows outside the   */
 /* matrix (the reference raises BoundsError there; they are skipped here).               */

@@ -68,6 +68,8 @@ def lib():
         L.orc_createdatamatrix.argtypes = [ip, ip, ip, dp, dp, i64, i64, i64, dp]
         L.orc_createdatamatrix.restype = i64
         L.orc_distancematrix.argtypes = [dp, dp, i64, dp]
+        L.orc_polygoncentroids.argtypes = [dp, dp, i64, i64, dp, dp, dp]
+        L.orc_polygoncentroids.restype = None
         _lib = L
     return _lib
 
@@ -125,6 +127,18 @@ def distancematrix(centroid_lat, centroid_long):
     out = np.zeros((lat.shape[0], lat.shape[0]), order="F")
     lib().orc_distancematrix(_p(lat), _p(lon), lat.shape[0], _p(out))
     return out
+
+
+def polygoncentroids(longitude_matrix, latitude_matrix):
+    """src/processgeodata.jl:99-148 -> (centroid_lat[N], centroid_long[N], area_polygon[N]).
+    The matrices are [N,V] zero-terminated vertex lists; copies are taken (the reference closes the rings in place)."""
+    lon = np.array(longitude_matrix, dtype=np.float64, order="F", copy=True)
+    lat = np.array(latitude_matrix, dtype=np.float64, order="F", copy=True)
+    assert lon.shape == lat.shape and lon.ndim == 2
+    N, V = lon.shape
+    c_lat, c_lon, area = np.zeros(N), np.zeros(N), np.zeros(N)
+    lib().orc_polygoncentroids(_p(lon), _p(lat), N, V, _p(c_lat), _p(c_lon), _p(area))
+    return c_lat, c_lon, area
 
 
 def createdatamatrix(sourceid, dstid, hod, mean, stddev, number_zones, *, T):

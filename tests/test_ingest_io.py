@@ -116,3 +116,82 @@ def test_device_distance_matrix_matches_oracle(ctx):
         want = O.distancematrix(lat, lon)
         np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)     # device cos() vs libm: a few ulp
         assert (np.diag(got) == 1).all() and np.array_equal(got, got.T)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# polygon area / centroid block of processgeodata (src/processgeodata.jl:99-148)
+# ---------------------------------------------------------------------------------------------------------
+def _polygon_matrices(rs, N, V, *, duplicate=True):
+    """Zero-terminated vertex lists the way the reference's GeoJSON walk fills them: a ring around a Melbourne-like
+    centre, every vertex stored twice (src/processgeodata.jl:44-47 runs once per coordinate of the pair)."""
+    lon, lat = np.zeros((N, V), order="F"), np.zeros((N, V), order="F")
+    rings = []
+    for i in range(N):
+        if i % 7 == 3:
+            rings.append(None)              # a zone id that never occurs in the file: row stays zero
+            continue
+        k = int(rs.integers(3, 40))
+        ang = np.sort(rs.random(k)) * 2 * np.pi
+        rad = 0.01 + 0.02 * rs.random(k)
+        x = 144.9 + 0.4 * rs.random() + rad * np.cos(ang)
+        y = -37.8 + 0.3 * rs.random() + rad * np.sin(ang)
+        x, y = np.append(x, x[0]), np.append(y, y[0])     # GeoJSON rings repeat the first vertex at the end
+        rings.append((x.copy(), y.copy()))
+        if duplicate:
+            x, y = np.repeat(x, 2), np.repeat(y, 2)
+        lon[i, :len(x)], lat[i, :len(y)] = x, y
+    return lon, lat, rings
+
+
+def test_oracle_polygon_centroids_match_the_shoelace_formulas():
+    rs = np.random.default_rng(11)
+    lon, lat, rings = _polygon_matrices(rs, 20, 200)
+    lon0, lat0 = lon.copy(), lat.copy()
+    c_lat, c_lon, area = O.polygoncentroids(lon, lat)
+    assert np.array_equal(lon, lon0) and np.array_equal(lat, lat0)        # the wrapper works on copies
+    for i, ring in enumerate(rings):
+        if ring is None:
+            assert c_lat[i] == 0 and c_lon[i] == 0 and area[i] == 0       # :105 skips zones without vertices
+            continue
+        x, y = ring
+        cross = x[:-1] * y[1:] - x[1:] * y[:-1]
+        A = cross.sum() / 2                                               # standard signed area (x = lon, y = lat)
+        cx = ((x[:-1] + x[1:]) * cross).sum() / (6 * A)
+        cy = ((y[:-1] + y[1:]) * cross).sum() / (6 * A)
+        np.testing.assert_allclose(area[i], -A, rtol=1e-6)                # the reference's sum is lat*lon' - lat'*lon
+        # the sums are differences of products of ~1e4-sized numbers: ~1e-7 degrees is what fp64 leaves
+        np.testing.assert_allclose(c_lon[i], cx, atol=1e-5)
+        np.testing.assert_allclose(c_lat[i], cy, atol=1e-5)
+        assert x.min() < c_lon[i] < x.max() and y.min() < c_lat[i] < y.max()
+
+
+def test_oracle_polygon_duplicate_vertices_do_not_move_the_centroid():
+    rs = np.random.default_rng(12)
+    lon2, lat2, _ = _polygon_matrices(rs, 10, 200, duplicate=True)
+    rs = np.random.default_rng(12)
+    lon1, lat1, _ = _polygon_matrices(rs, 10, 200, duplicate=False)
+    a, b = O.polygoncentroids(lon2, lat2), O.polygoncentroids(lon1, lat1)
+    for u, v in zip(a, b):
+        np.testing.assert_allclose(u, v, rtol=0, atol=1e-9)               # a repeated vertex adds exact zeros
+
+
+@pytest.mark.gpu
+def test_device_polygon_centroids_match_oracle(ctx):
+    from carparkingmaps_b200 import api
+    rs = np.random.default_rng(13)
+    for N, V in ((1, 50), (9, 120), (300, 90)):
+        lon, lat, _ = _polygon_matrices(rs, N, V)
+        if N == 9:
+            lon[5, 4] = 0.0                   # an embedded zero longitude: the area pass stops there, the centroid pass does not
+        lon0 = lon.copy()
+        got = api.polygoncentroids(lon, lat)
+        want = O.polygoncentroids(lon, lat)
+        assert np.array_equal(lon, lon0)      # host inputs untouched
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w, equal_nan=True)                   # same operations in the same order: bit-exact
+    # a row without a terminator inside the window: both sides stop at the last column
+    lon, lat, _ = _polygon_matrices(rs, 4, 30)
+    lon[0, :], lat[0, :] = 145.0 + 0.01 * rs.random(30), -37.8 + 0.01 * rs.random(30)
+    got, want = api.polygoncentroids(lon, lat), O.polygoncentroids(lon, lat)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w, equal_nan=True)
