@@ -19,7 +19,7 @@
 module CarParkingMapsGPU
 
 export createpdrive, createpdestin, initializestates, solveinitialvalueproblem, resampling,
-       averagedrivingtime, correctparameters, zonehistogram, sampledataset, cpm_seed!
+       averagedrivingtime, correctparameters, zonehistogram, sampledataset, polygoncentroids, distancematrix, cpm_seed!
 
 const LIBCPM = get(ENV, "LIBCPM", joinpath(@__DIR__, "..", "libcpm.so"))
 
@@ -153,6 +153,25 @@ function zonehistogram(number_zones, state_matrix::Array{Int64,2}, transition_ma
                 (Ptr{Cvoid}, Ptr{Int64}, Ptr{Float64}, Int64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 ctx(), state_matrix, transition_matrix, Int64(C), N, T, parking_cars, driving_cars, traffic))
     return parking_cars, driving_cars, traffic
+end
+
+# the polygon block of processgeodata (src/processgeodata.jl:99-148): zero-terminated vertex lists -> centroids, areas
+function polygoncentroids(longitude_matrix::Array{Float64,2}, latitude_matrix::Array{Float64,2})
+    N, V = size(longitude_matrix)
+    centroid_lat, centroid_long, area_polygon = zeros(N, 1), zeros(N, 1), zeros(N, 1)
+    check(ccall((:cpm_polygon_centroids, LIBCPM), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                ctx(), longitude_matrix, latitude_matrix, Int64(N), Int64(V), centroid_lat, centroid_long, area_polygon))
+    return centroid_lat, centroid_long, area_polygon
+end
+
+# the distance block of processgeodata (src/processgeodata.jl:150-166)
+function distancematrix(centroid_lat, centroid_long)
+    N = length(centroid_lat)
+    distance_matrix_km = zeros(N, N)
+    check(ccall((:cpm_distance_matrix, LIBCPM), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}),
+                ctx(), vec(Float64.(centroid_lat)), vec(Float64.(centroid_long)), Int64(N), distance_matrix_km))
+    return distance_matrix_km
 end
 
 # main.jl:82-98 in ONE call, device-resident: only datamatrix / distance matrix go up and the reduced results
