@@ -76,6 +76,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N_PENDING>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
 
+// pull [src, src + bytes) towards L2 (bytes a multiple of 16, src 16-byte aligned); no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 // one lane of a converged warp (elect.sync): lets the compiler issue TMA instructions straight from uniform registers
 __device__ __forceinline__ bool elect_one()
 {

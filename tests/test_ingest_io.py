@@ -130,7 +130,7 @@ def _polygon_matrices(rs, N, V, *, duplicate=True):
         if i % 7 == 3:
             rings.append(None)              # a zone id that never occurs in the file: row stays zero
             continue
-        k = int(rs.integers(3, 40))
+        k = int(rs.integers(3, max(4, min(40, V // 2 - 2))))   # the doubled, closed ring and its terminator fit in V
         ang = np.sort(rs.random(k)) * 2 * np.pi
         rad = 0.01 + 0.02 * rs.random(k)
         x = 144.9 + 0.4 * rs.random() + rad * np.cos(ang)
