@@ -326,7 +326,7 @@ __device__ double jl_sum_strided(const double *__restrict__ x, int64_t n, int64_
         for (; k < n; ++k) s += x[k * stride];
         return s;
     }
-    const int64_t h = n / 2;
+    const int64_t h = (n + 1) / 2;   // imid = (ifirst + ilast) >> 1: the first half gets ceil(n/2) elements (base/reduce.jl)
     const double a = jl_sum_strided(x, h, stride);
     return a + jl_sum_strided(x + h * stride, n - h, stride);
 }

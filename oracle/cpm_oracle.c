@@ -135,7 +135,10 @@ static double jl_pow(double x, double e)
     return pow(x, e);
 }
 
-/* Julia's sum(::Vector{Float64}) is pairwise with a 1024-element sequential base case. */
+/* Julia's sum(::Vector{Float64}) = Base.mapreduce_impl(identity, +, A, 1, n, 1024) (base/reduce.jl): ranges of at  */
+/* most 1024 elements are added left to right, longer ones split at imid = (ifirst + ilast) >> 1, i.e. the FIRST   */
+/* half gets ceil(n/2) elements.  (The sequential part is a @simd loop in Julia, whose association order is up to   */
+/* LLVM: "parity unpinned at the ulp level")                                                           */
 static double jl_sum(const double *x, i64 n)
 {
     if (n <= 1024) {
@@ -143,9 +146,10 @@ static double jl_sum(const double *x, i64 n)
         for (i64 k = 0; k < n; ++k) s += x[k];
         return s;
     }
-    i64 h = n / 2;
+    i64 h = (n + 1) / 2;
     return jl_sum(x, h) + jl_sum(x + h, n - h);
 }
+double orc_jl_sum(const double *x, i64 n) { return jl_sum(x, n); }   /* exported for tests */
 
 /* Julia maximum/minimum propagate NaN. */
 static double jl_max(const double *x, i64 n)

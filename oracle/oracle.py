@@ -70,6 +70,8 @@ def lib():
         L.orc_distancematrix.argtypes = [dp, dp, i64, dp]
         L.orc_polygoncentroids.argtypes = [dp, dp, i64, i64, dp, dp, dp]
         L.orc_polygoncentroids.restype = None
+        L.orc_jl_sum.argtypes = [dp, i64]
+        L.orc_jl_sum.restype = C.c_double
         _lib = L
     return _lib
 
@@ -127,6 +129,12 @@ def distancematrix(centroid_lat, centroid_long):
     out = np.zeros((lat.shape[0], lat.shape[0]), order="F")
     lib().orc_distancematrix(_p(lat), _p(lon), lat.shape[0], _p(out))
     return out
+
+
+def jl_sum(x):
+    """Julia's sum(::Vector{Float64}): pairwise above 1024 elements (base/reduce.jl mapreduce_impl)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    return float(lib().orc_jl_sum(_p(x), x.shape[0]))
 
 
 def polygoncentroids(longitude_matrix, latitude_matrix):

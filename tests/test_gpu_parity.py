@@ -46,6 +46,25 @@ def test_createpdrive_createpdestin(ctx, N, density, seed, e_drive, e_dest):
         np.testing.assert_array_equal(got_pd, pd)
 
 
+@pytest.mark.parametrize("N", [1027, 2050, 2051])
+def test_createpdestin_pairwise_norm_above_1024_zones(ctx, N):
+    """Above 1,024 zones Julia's `sum` (src/createpdestin.jl:33) is pairwise, the first half taking ceil(n/2) elements;
+    odd (sub-)ranges make the split position matter (2050 -> 1025 + 1025 -> 513 + 512).  Even N takes the TMA path
+    of the mean sums, odd N the plain-load fallback."""
+    Tn = 2
+    dm, dist = synth_city(N, Tn, seed=N, density=0.7)
+    _set_globals()
+    api.T = Tn
+    try:
+        got_px = api.createpdestin(dm, N)
+        got_pd = api.createpdrive(dm, dist, N)
+    finally:
+        api.T = T
+    np.testing.assert_array_equal(got_px, O.createpdestin(dm, N, T=Tn, e_dest=2))
+    np.testing.assert_allclose(got_pd, O.createpdrive(dm, dist, N, T=Tn, p_min=0.1, p_max=0.9, e_drive=0.5), rtol=TAB_RTOL,
+                               atol=0, equal_nan=True)
+
+
 def test_tables_edge_cases(ctx):
     dm, dist = edge_case_city(T)
     _set_globals()

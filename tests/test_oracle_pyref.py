@@ -154,3 +154,28 @@ def test_day_counts_matches_trajectory_functions():
     np.testing.assert_array_equal(parking, np.rint(pk * C).astype(np.int64))
     np.testing.assert_array_equal(driving, dr.astype(np.int64))
     np.testing.assert_allclose(tsum, tr[:, :, 2].sum(), rtol=1e-12)
+
+
+def _mapreduce_impl(a, ifirst, ilast, blksize=1024):
+    """Base.mapreduce_impl(identity, +, A, ifirst, ilast, 1024) of base/reduce.jl, 1-based, sequential base case."""
+    if ifirst == ilast:
+        return a[ifirst - 1]
+    if ifirst + blksize > ilast:
+        v = a[ifirst - 1] + a[ifirst]
+        for i in range(ifirst + 2, ilast + 1):
+            v = v + a[i - 1]
+        return v
+    imid = (ifirst + ilast) >> 1
+    return _mapreduce_impl(a, ifirst, imid, blksize) + _mapreduce_impl(a, imid + 1, ilast, blksize)
+
+
+def test_jl_sum_follows_julias_pairwise_split():
+    """The norm of createpdestin (:33) and averagedrivingtime (:7) are Julia `sum`s: pairwise above 1024 elements,
+    the first half taking ceil(n/2).  Values are chosen so that any other association order changes the result."""
+    rs = np.random.default_rng(3)
+    for n in (1, 2, 7, 1024, 1025, 2049, 2400, 3001, 4097):
+        x = rs.random(n) * 10.0 ** rs.integers(-8, 8, n)
+        want = float(_mapreduce_impl([float(v) for v in x], 1, n))
+        assert O.jl_sum(x) == want, n
+    x = rs.random(3001) * 10.0 ** rs.integers(-8, 8, 3001)
+    assert O.jl_sum(x) == float(O.jl_sum(x[:1501])) + float(O.jl_sum(x[1501:]))
