@@ -331,6 +331,9 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             for hnd in pins:
                 lib.cpm_host_free(hnd)
 
+    if os.environ.get("CPM_BENCH_DEBUG"):
+        print(f"[rank {rank}] device {torch.cuda.current_device()} {torch.cuda.get_device_properties(local_rank).uuid} ms/step {ms / args.steps:.3f} "
+              f"e2e ms/step {e2e_ms / e2e_steps:.3f} cpus {len(os.sched_getaffinity(0))}", file=sys.stderr, flush=True)
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist_.all_reduce(t, op=dist_.ReduceOp.MAX)
