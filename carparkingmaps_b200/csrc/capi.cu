@@ -81,6 +81,8 @@ struct cpm_ctx {
     bool profiling = false;
     uint64_t prof_tick = 0;
     cudaStream_t copy_st = nullptr;          // host-input pipeline: uploads overlap the tables and the IVP
+    cudaStream_t aux_st = nullptr;           // dataset pass: createpdrive runs beside the CDF build
+    cudaEvent_t ev_aux[2] = {nullptr, nullptr};   // fork (main -> aux), join (aux -> main)
     cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> ev;      // start0, stop0, start1, stop1, ...
     std::vector<int64_t> ev_launches; // step-kernel launches bracketed by each pair
@@ -172,6 +174,7 @@ extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     ctx->traj_state.release(); ctx->traj_trans.release(); ctx->tmp.release(); ctx->partials.release(); ctx->scalars.release();
     for (auto &b : ctx->u) b.release();
+    if (ctx->aux_st) { cudaStreamSynchronize(ctx->aux_st); cudaStreamDestroy(ctx->aux_st); for (auto e : ctx->ev_aux) if (e) cudaEventDestroy(e); }
     if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); for (auto e : ctx->ev_copy) if (e) cudaEventDestroy(e); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -181,6 +184,7 @@ extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
 extern "C" int32_t cpm_ctx_sync(cpm_ctx *ctx)
 {
     TRY(use(ctx));
+    if (ctx->aux_st) CU(cudaStreamSynchronize(ctx->aux_st));
     CU(cudaStreamSynchronize(ctx->st));
     return CPM_OK;
 }
@@ -259,6 +263,7 @@ extern "C" int32_t cpm_city_destroy(cpm_city *c)
 {
     if (!c) return CPM_OK;
     cudaSetDevice(c->ctx->device);
+    if (c->ctx->aux_st) cudaStreamSynchronize(c->ctx->aux_st);   // a failed pass may have left the createpdrive chain unjoined
     cudaStreamSynchronize(c->ctx->st);
     c->dm.release(); c->dist.release(); c->rdist.release(); c->msd.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
     c->norm.release(); c->cdf.release(); c->rowzero.release();
@@ -343,8 +348,9 @@ extern "C" int32_t cpm_city_download_inputs(cpm_city *c, double *datamatrix, dou
     return CPM_OK;
 }
 
-static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, double e_drive)
+static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, double e_drive, cudaStream_t st = nullptr)
 {
+    if (!st) st = c->ctx->st;
     if (!c->have_inputs) return fail(CPM_ERR_STATE, "createpdrive needs the city inputs (upload or synth first)");
     const size_t NT = (size_t)c->N * c->T;
     TRY(c->mean_sum.ensure(NT * sizeof(double)));
@@ -352,10 +358,10 @@ static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, 
     TRY(c->p_drive.ensure(NT * sizeof(double)));
     if (!c->have_meansum) {   // parameter-independent: cached across sweeps
         LAUNCH(c->ctx, launch_pdrive_meansum(c->dm.as<double>(), c->dist.as<double>(), c->rdist.as<double>(), c->N, c->T,
-                                             c->mean_sum.as<double>(), c->ctx->st));
+                                             c->mean_sum.as<double>(), st));
         c->have_meansum = true;
     }
-    LAUNCH(c->ctx, launch_pdrive_finish(c->mean_sum.as<double>(), c->N, c->T, p_min, p_max, e_drive, c->p_drive.as<double>(), c->ctx->st));
+    LAUNCH(c->ctx, launch_pdrive_finish(c->mean_sum.as<double>(), c->N, c->T, p_min, p_max, e_drive, c->p_drive.as<double>(), st));
     c->have_pdrive = true;
     return CPM_OK;
 }
@@ -374,7 +380,7 @@ static int32_t city_alloc_cdf(cpm_city *c)
     TRY(c->rowzero.ensure((size_t)c->N * c->T));
     return CPM_OK;
 }
-static int32_t city_build_pdestin_async(cpm_city *c, double e_dest, bool write_p = true)
+static int32_t city_build_pdestin_async(cpm_city *c, double e_dest, bool write_p = true, cudaEvent_t before_cdf = nullptr)
 {
     if (!c->have_inputs) return fail(CPM_ERR_STATE, "createpdestin needs the city inputs (upload or synth first)");
     const size_t NN = (size_t)c->N * c->N;
@@ -382,6 +388,7 @@ static int32_t city_build_pdestin_async(cpm_city *c, double e_dest, bool write_p
     TRY(c->norm.ensure((size_t)c->N * c->T * sizeof(double)));
     TRY(city_alloc_cdf(c));
     LAUNCH(c->ctx, launch_pdestin(c->dm.as<double>(), c->N, c->T, e_dest, c->p_dest.as<double>(), c->norm.as<double>(), c->ctx->st));
+    if (before_cdf) CU(cudaEventRecord(before_cdf, c->ctx->st));   // the two streaming passes are done: HBM has headroom from here
     LAUNCH(c->ctx, launch_cdf_normalise(c->p_dest.as<double>(), c->norm.as<double>(), c->N, c->T, c->cdf.as<double>(),
                                         c->ldc, c->goff, c->G, c->rowzero.as<uint8_t>(), write_p ? 1 : 0, c->ctx->st));
     c->have_cdf = true;
@@ -788,8 +795,18 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     city->have_meansum = false;   // one dataset pass recomputes everything, like the reference (no cached stages)
     TRY(fleet->lost_acc.ensure(sizeof(unsigned long long)));
     CU(cudaMemsetAsync(fleet->lost_acc.p, 0, sizeof(unsigned long long), ctx->st));
-    TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive));                 // main.jl:82
-    TRY(city_build_pdestin_async(city, pr->e_dest, false));                                 // main.jl:85
+    // createpdrive (main.jl:82) and createpdestin (main.jl:85) are independent.  k_pdest_unnorm / k_pdest_norm run at
+    // the HBM roofline, k_cdf_build at about half of it (bound by its transposing writes): the createpdrive chain runs
+    // on a second stream from the moment the CDF build starts and uses the bandwidth that kernel leaves idle.
+    if (!ctx->aux_st) {
+        CU(cudaStreamCreateWithFlags(&ctx->aux_st, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev_aux) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    TRY(city_build_pdestin_async(city, pr->e_dest, false, ctx->ev_aux[0]));                 // main.jl:85
+    CU(cudaStreamWaitEvent(ctx->aux_st, ctx->ev_aux[0], 0));
+    TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive, ctx->aux_st));     // main.jl:82
+    CU(cudaEventRecord(ctx->ev_aux[1], ctx->aux_st));
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_aux[1], 0));
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->st));   // main.jl:88
     fleet->car_offset = 0; fleet->zone_valid = true; fleet->bucket_valid = false;
     cpm_day_opts o;
