@@ -73,7 +73,7 @@ __device__ __forceinline__ int zone_of_slot(const uint32_t *__restrict__ start, 
 // ------------------------------------------------------------------------------------------------
 // k_bucket_sample
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int CH>
+template <int THREADS, int CH, bool INJ>   // INJ: uniform variates injected by the caller (parity tests) instead of Philox
 __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
     const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
     const double *__restrict__ pd_t = a.p_drive + N * a.hour;
     const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
-    const bool inj = a.rng.mode == 1;
+    constexpr bool inj = INJ;
     const int64_t uoff = a.rng.ld * a.step;
     uint32_t *const hist = s.hist;
 
@@ -556,13 +556,14 @@ int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
 {
     size_t smem = 0; int ctas = 0;
     const int shape = bucket_shape(a.N, a.ldc, &smem, &ctas);
-    static size_t granted[3] = {0, 0, 0};
+    static size_t granted[4] = {0, 0, 0, 0};
+    const bool inj = a.rng.mode == 1;
     if (shape == 1) {
-        ensure_smem(k_bucket_sample<256, 1024>, smem, granted[1]);
-        launch_pdl(k_bucket_sample<256, 1024>, G, 256, smem, st, a);
+        if (inj) { ensure_smem(k_bucket_sample<256, 1024, true>, smem, granted[0]); launch_pdl(k_bucket_sample<256, 1024, true>, G, 256, smem, st, a); }
+        else     { ensure_smem(k_bucket_sample<256, 1024, false>, smem, granted[1]); launch_pdl(k_bucket_sample<256, 1024, false>, G, 256, smem, st, a); }
     } else if (shape == 2) {
-        ensure_smem(k_bucket_sample<512, 2048>, smem, granted[2]);
-        launch_pdl(k_bucket_sample<512, 2048>, G, 512, smem, st, a);
+        if (inj) { ensure_smem(k_bucket_sample<512, 2048, true>, smem, granted[2]); launch_pdl(k_bucket_sample<512, 2048, true>, G, 512, smem, st, a); }
+        else     { ensure_smem(k_bucket_sample<512, 2048, false>, smem, granted[3]); launch_pdl(k_bucket_sample<512, 2048, false>, G, 512, smem, st, a); }
     } else return -1;
     return 1;
 }
