@@ -77,8 +77,25 @@ __device__ __forceinline__ double truncnormal(double mu, double sigma, double u)
     double lo = 0.9 * mu, hi = 1.1 * mu;
     const double b = (0.1 * mu) / sigma;
     const double E = erf(b / 1.41421356237309504880);
-    const double w = 2.0 * u - 1.0;
-    const double z = 1.41421356237309504880 * erfinv(w * E);
+    // z = sqrt(2) * erfinv((2u-1) * E) = Phi^-1(1/2 + q), q = (u - 1/2) * E.  For |q| <= 0.425 (every draw when
+    // E <= 0.85, i.e. sigma > 0.07 mu; most draws otherwise) Wichura's AS 241 central rational (PPND16, |error| ~ 1e-16)
+    // gives it in two degree-7 Horner chains and one division instead of erfinv's logarithm + branch cascade.
+    const double q = (u - 0.5) * E;
+    double z;
+    if (fabs(q) <= 0.425) {
+        const double r = 0.180625 - q * q;
+        double A = 2509.0809287301226727, B = 5226.4952788528545610;
+        A = fma(A, r, 33430.575583588128105); B = fma(B, r, 28729.085735721942674);
+        A = fma(A, r, 67265.770927008700853); B = fma(B, r, 39307.895800092710610);
+        A = fma(A, r, 45921.953931549871457); B = fma(B, r, 21213.794301586595867);
+        A = fma(A, r, 13731.693765509461125); B = fma(B, r, 5394.1960214247511077);
+        A = fma(A, r, 1971.5909503065514427); B = fma(B, r, 687.18700749205790830);
+        A = fma(A, r, 133.14166789178437745); B = fma(B, r, 42.313330701600911252);
+        A = fma(A, r, 3.3871328727963666080); B = fma(B, r, 1.0);
+        z = q * A / B;
+    } else {
+        z = 1.41421356237309504880 * erfinv(2.0 * q);
+    }
     double x = mu + sigma * z;
     if (lo > hi) { const double t = lo; lo = hi; hi = t; }
     if (x < lo) x = lo;
