@@ -69,6 +69,39 @@ __device__ __forceinline__ double jl_pow(double x, double e)
     return pow(x, e);
 }
 
+// erf(x) for |x| <= 1.5 by its Maclaurin series x * sum_n (2/sqrt(pi)) (-1)^n x^(2n) / (n! (2n+1)), 24 terms in Horner form
+// (relative error < 5e-16 on that range, checked against scipy.special.erf).  One straight-line chain: the library erf()
+// switches between a polynomial and an exp-based branch at |x| = 1, and a warp whose lanes straddle 1 pays for both.
+__device__ __forceinline__ double erf_small(double x)
+{
+    const double t = x * x;
+    double p = -9.28672901131906e-25;
+    p = fma(p, t, 2.2308786802746453e-23);
+    p = fma(p, t, -5.136209054585811e-22);
+    p = fma(p, t, 1.131218725924631e-20);
+    p = fma(p, t, -2.3784598852774293e-19);
+    p = fma(p, t, 4.763348040515068e-18);
+    p = fma(p, t, -9.063970842808673e-17);
+    p = fma(p, t, 1.6342614095367152e-15);
+    p = fma(p, t, -2.7835162072109212e-14);
+    p = fma(p, t, 4.4632242632864775e-13);
+    p = fma(p, t, -6.7113668551641105e-12);
+    p = fma(p, t, 9.422759064650411e-11);
+    p = fma(p, t, -1.2290555301717926e-09);
+    p = fma(p, t, 1.4807192815879218e-08);
+    p = fma(p, t, -1.6365844691234924e-07);
+    p = fma(p, t, 1.6462114365889246e-06);
+    p = fma(p, t, -1.492565035840625e-05);
+    p = fma(p, t, 0.00012055332981789664);
+    p = fma(p, t, -0.0008548327023450852);
+    p = fma(p, t, 0.005223977625442188);
+    p = fma(p, t, -0.026866170645131252);
+    p = fma(p, t, 0.11283791670955126);
+    p = fma(p, t, -0.37612638903183754);
+    p = fma(p, t, 1.1283791670955126);
+    return x * p;
+}
+
 // Truncated(Normal(mu, sigma), 0.9mu, 1.1mu) by inverse CDF from one uniform (src/resampling.jl:68,74).
 // Symmetric interval: z = sqrt(2) * erfinv((2u-1) * erf(b/sqrt(2))), b = 0.1*mu/sigma.
 __device__ __forceinline__ double truncnormal(double mu, double sigma, double u)
@@ -76,7 +109,8 @@ __device__ __forceinline__ double truncnormal(double mu, double sigma, double u)
     if (!(sigma > 0.0) || isinf(sigma) || isinf(mu) || isnan(mu)) return mu;
     double lo = 0.9 * mu, hi = 1.1 * mu;
     const double b = (0.1 * mu) / sigma;
-    const double E = erf(b / 1.41421356237309504880);
+    const double xe = b / 1.41421356237309504880;
+    const double E = (fabs(xe) <= 1.5) ? erf_small(xe) : erf(xe);
     // z = sqrt(2) * erfinv((2u-1) * E) = Phi^-1(1/2 + q), q = (u - 1/2) * E.  For |q| <= 0.425 (every draw when
     // E <= 0.85, i.e. sigma > 0.07 mu; most draws otherwise) Wichura's AS 241 central rational (PPND16, |error| ~ 1e-16)
     // gives it in two degree-7 Horner chains and one division instead of erfinv's logarithm + branch cascade.
