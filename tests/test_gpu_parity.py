@@ -65,6 +65,21 @@ def test_createpdestin_pairwise_norm_above_1024_zones(ctx, N):
                                atol=0, equal_nan=True)
 
 
+@pytest.mark.parametrize("N,Tn", [(130, 3), (64, 5), (34, 1), (2, 7)])
+def test_tables_with_an_odd_number_of_hours(ctx, N, Tn):
+    """The TMA mean-sum kernel pairs hours (two chains per lane) when T is even and takes one hour per lane otherwise."""
+    dm, dist = synth_city(N, Tn, seed=N + Tn, density=0.6)
+    _set_globals()
+    api.T = Tn
+    try:
+        got_pd, got_px = api.createpdrive(dm, dist, N), api.createpdestin(dm, N)
+    finally:
+        api.T = T
+    np.testing.assert_allclose(got_pd, O.createpdrive(dm, dist, N, T=Tn, p_min=0.1, p_max=0.9, e_drive=0.5), rtol=TAB_RTOL,
+                               atol=0, equal_nan=True)
+    np.testing.assert_array_equal(got_px, O.createpdestin(dm, N, T=Tn, e_dest=2))
+
+
 def test_tables_edge_cases(ctx):
     dm, dist = edge_case_city(T)
     _set_globals()
