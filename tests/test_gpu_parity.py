@@ -294,6 +294,33 @@ def test_sample_dataset_matches_oracle_pipeline(ctx, N, cpz, density):
     city.close(); fleet.close()
 
 
+@pytest.mark.parametrize("N,cpz,Tn", [(1, 1, 24), (1, 7, 24), (2, 1, 24), (3, 2, 2), (4, 5, 1), (2, 33, 3)])
+def test_sample_dataset_degenerate_shapes(ctx, N, cpz, Tn):
+    """One zone (every trip is a 5-minute same-zone trip or no trip at all), one car, one hour (no IVP steps at all):
+    the whole pass against the oracle, both samplers."""
+    from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_GATHER
+    C = N * cpz
+    dm, dist = synth_city(N, Tn, seed=N * 100 + cpz, density=1.0)
+    pd = O.createpdrive(dm, dist, N, T=Tn, p_min=0.1, p_max=0.9, e_drive=0.5)
+    px = O.createpdestin(dm, N, T=Tn, e_dest=2)
+    zone = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
+    if Tn > 1:
+        O.day_counts(zone, N, Tn, Tn - 1, 1, pd, px, dm, dist, O.Rng(mode="philox", seed=5, stream=0), False)
+    pk0, dr0, ts0, lost0 = O.day_counts(zone, N, Tn, Tn, 1, pd, px, dm, dist, O.Rng(mode="philox", seed=5, stream=1), True)
+    tot = dr0.sum(axis=0).astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        traffic0 = (tot - tot.min()) / (tot.max() - tot.min())            # 0/0 -> NaN when every hour has the same count
+    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER):
+        city = City(ctx, N, Tn).upload(dm, dist)
+        fleet = Fleet(ctx, C)
+        parking, traffic, A, lost = sample_dataset(city, fleet, cars_per_zone=cpz, seed=5, sampler=sampler)
+        assert lost == lost0
+        np.testing.assert_array_equal(parking, pk0 / C)
+        np.testing.assert_array_equal(traffic, traffic0)
+        np.testing.assert_allclose(A, ts0 / (C * Tn * 3600.0), rtol=TIME_RTOL)
+        city.close(); fleet.close()
+
+
 def test_device_synth_is_bit_identical_to_numpy(ctx):
     for N, seed, density in [(37, 0, 1.0), (64, 5, 0.09)]:
         dm, dist = synth_city(N, T, seed=seed, density=density)
