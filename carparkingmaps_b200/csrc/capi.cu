@@ -549,6 +549,15 @@ extern "C" int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src)
     if (!src->zone_valid) return fail(CPM_ERR_STATE, "source fleet zones are not materialised");
     CU(cudaMemcpyAsync(dst->zone.p, src->zone.p, (size_t)dst->C * sizeof(int32_t), cudaMemcpyDeviceToDevice, dst->ctx->st));
     dst->zone_valid = true; dst->bucket_valid = false;
+    if (src->bucket_valid) {   // the source is grouped by zone already: take its grouping instead of redoing it per copy
+        const size_t NB = (size_t)src->bucket_N + 1;
+        TRY(dst->perm[0].ensure((size_t)dst->C * 4));
+        TRY(dst->cnt_cur.ensure(NB * 4)); TRY(dst->start_tmp.ensure((NB + 1) * 4));
+        CU(cudaMemcpyAsync(dst->perm[0].p, src->perm[src->cur].p, (size_t)dst->C * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
+        CU(cudaMemcpyAsync(dst->cnt_cur.p, src->cnt_cur.p, NB * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
+        CU(cudaMemcpyAsync(dst->start_tmp.p, src->start_tmp.p, (NB + 1) * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
+        dst->cur = 0; dst->bucket_valid = true; dst->bucket_N = src->bucket_N;
+    }
     return CPM_OK;
 }
 
@@ -629,6 +638,22 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
 }
 
 // bucket sampler: cars grouped by zone, CDF rows staged in shared memory (bucket.cu)
+// Group the cars of a fleet by zone from its car-id indexed zone array: perm[0] (car ids by bin), the bucket starts and
+// the bucket sizes (cnt_cur).  Leaves the fleet in the state a finished bucket day leaves it in.
+static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N)
+{
+    cpm_ctx *ctx = f->ctx;
+    const int NB = (int)N + 1;
+    if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
+    TRY(f->perm[0].ensure((size_t)f->C * 4));
+    TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
+    f->cur = 0;
+    LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), f->C, NB, f->cnt_cur.as<uint32_t>(), f->start_tmp.as<uint32_t>(),
+                                 f->cursor_tmp.as<uint32_t>(), f->perm[0].as<int32_t>(), ctx->st));
+    f->bucket_valid = true; f->bucket_N = N;
+    return CPM_OK;
+}
+
 static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
 {
     cpm_ctx *ctx = f->ctx;
@@ -644,15 +669,9 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
     uint32_t *bcnt = f->bcnt.as<uint32_t>(), *bdrv = f->bdrv.as<uint32_t>(), *start = f->start_tmp.as<uint32_t>();
     CU(cudaMemsetAsync(bdrv, 0, (size_t)S * NB * 4, ctx->st));
-    if (f->bucket_valid && f->bucket_N == N) {
-        // still grouped from the previous day: bucket sizes and bucket starts are current
-        CU(cudaMemcpyAsync(bcnt, f->cnt_cur.p, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
-    } else {
-        if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
-        f->cur = 0;
-        LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), C, NB, bcnt, start, f->cursor_tmp.as<uint32_t>(),
-                                     f->perm[0].as<int32_t>(), ctx->st));
-    }
+    if (!(f->bucket_valid && f->bucket_N == N)) TRY(fleet_bucketize_async(f, N));
+    // grouped (from the previous day, a copy of a grouped fleet, or just now): bucket sizes and bucket starts are current
+    CU(cudaMemcpyAsync(bcnt, f->cnt_cur.p, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
     Scalars *sc = f->scalars.as<Scalars>();
     BucketArgs a;
     memset(&a, 0, sizeof a);
@@ -905,6 +924,8 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
     if (rc == CPM_OK) rc = cpm_fleet_create(ctx, C, &work);
     if (rc == CPM_OK) rc = cpm_fleet_set_zones(base, initial_zones);
     if (rc == CPM_OK && P >= 2) rc = cpm_city_prepare_multi_day(city);   // many days on the same inputs
+    // every set starts from the same state: group it by zone once, the per-set copy takes the grouping along
+    if (rc == CPM_OK && P >= 2 && city_alloc_cdf(city) == CPM_OK && city->G > 0 && bucket_supported(N, city->ldc)) rc = fleet_bucketize_async(base, N);
     std::vector<unsigned long long> tc((size_t)T);
     bool have_e_dest = false;
     double cur_e_dest = 0.0;
