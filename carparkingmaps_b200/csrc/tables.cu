@@ -355,16 +355,18 @@ __global__ void __launch_bounds__(64) k_pdest_norm(const double *__restrict__ p_
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ double div_slow(double a, double d) { return a / d; }
 
+constexpr int kCdfWarps = 1;   // warps per CTA: one, so that the N*T/32 row groups spread evenly over the SMs
+
 template <bool DIVIDE, bool WRITE_P>
-__global__ void __launch_bounds__(128) k_cdf_build(double *__restrict__ p_dest, const double *__restrict__ norm, int64_t N,
+__global__ void __launch_bounds__(32 * kCdfWarps) k_cdf_build(double *__restrict__ p_dest, const double *__restrict__ norm, int64_t N,
                                                    int64_t T, double *__restrict__ cdf, int64_t ldc, int goff, int G,
                                                    uint8_t *__restrict__ rowzero)
 {
-    __shared__ double tile[4][32][33];
-    __shared__ uint16_t gidx[4][32][34];   // guide cell reached by each running sum: min(G, floor(run * G)); 0 for NaN
-    __shared__ uint16_t gcarry[4][32];
+    __shared__ double tile[kCdfWarps][32][33];
+    __shared__ uint16_t gidx[kCdfWarps][32][34];   // guide cell reached by each running sum: min(G, floor(run * G)); 0 for NaN
+    __shared__ uint16_t gcarry[kCdfWarps][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t i0 = ((int64_t)blockIdx.x * 4 + w) * 32;
+    const int64_t i0 = ((int64_t)blockIdx.x * kCdfWarps + w) * 32;
     const int64_t t = blockIdx.y;
     if (i0 >= N) return;
     const int64_t i = i0 + lane;
@@ -511,17 +513,17 @@ int launch_pdestin(const double *dm, int64_t N, int64_t T, double e_dest, double
 int launch_cdf_from_pdest(const double *p_dest, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff, int G,
                           uint8_t *rowzero, cudaStream_t st)
 {
-    dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
-    k_cdf_build<false, false><<<g, 128, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, ldc, goff, G, rowzero);
+    dim3 g((unsigned)((N + 32 * kCdfWarps - 1) / (32 * kCdfWarps)), (unsigned)T);
+    k_cdf_build<false, false><<<g, 32 * kCdfWarps, 0, st>>>(const_cast<double *>(p_dest), nullptr, N, T, cdf, ldc, goff, G, rowzero);
     return 1;
 }
 
 int launch_cdf_normalise(double *p_dest, const double *norm, int64_t N, int64_t T, double *cdf, int64_t ldc, int goff,
                          int G, uint8_t *rowzero, int write_p, cudaStream_t st)
 {
-    dim3 g((unsigned)((N + 127) / 128), (unsigned)T);
-    if (write_p) k_cdf_build<true, true><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, goff, G, rowzero);
-    else         k_cdf_build<true, false><<<g, 128, 0, st>>>(p_dest, norm, N, T, cdf, ldc, goff, G, rowzero);
+    dim3 g((unsigned)((N + 32 * kCdfWarps - 1) / (32 * kCdfWarps)), (unsigned)T);
+    if (write_p) k_cdf_build<true, true><<<g, 32 * kCdfWarps, 0, st>>>(p_dest, norm, N, T, cdf, ldc, goff, G, rowzero);
+    else         k_cdf_build<true, false><<<g, 32 * kCdfWarps, 0, st>>>(p_dest, norm, N, T, cdf, ldc, goff, G, rowzero);
     return 1;
 }
 
