@@ -640,16 +640,17 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
 // bucket sampler: cars grouped by zone, CDF rows staged in shared memory (bucket.cu)
 // Group the cars of a fleet by zone from its car-id indexed zone array: perm[0] (car ids by bin), the bucket starts and
 // the bucket sizes (cnt_cur).  Leaves the fleet in the state a finished bucket day leaves it in.
-static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N)
+static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N, cudaStream_t st = nullptr)
 {
     cpm_ctx *ctx = f->ctx;
+    if (!st) st = ctx->st;
     const int NB = (int)N + 1;
     if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
     TRY(f->perm[0].ensure((size_t)f->C * 4));
     TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
     f->cur = 0;
     LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), f->C, NB, f->cnt_cur.as<uint32_t>(), f->start_tmp.as<uint32_t>(),
-                                 f->cursor_tmp.as<uint32_t>(), f->perm[0].as<int32_t>(), ctx->st));
+                                 f->cursor_tmp.as<uint32_t>(), f->perm[0].as<int32_t>(), st));
     f->bucket_valid = true; f->bucket_N = N;
     return CPM_OK;
 }
@@ -824,10 +825,12 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     TRY(city_build_pdestin_async(city, pr->e_dest, false, ctx->ev_aux[0]));                 // main.jl:85
     CU(cudaStreamWaitEvent(ctx->aux_st, ctx->ev_aux[0], 0));
     TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive, ctx->aux_st));     // main.jl:82
+    // initializestates (main.jl:88) and the grouping of the cars by zone do not depend on the tables: second stream as well
+    LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->aux_st));
+    fleet->car_offset = 0; fleet->zone_valid = true; fleet->bucket_valid = false;
+    if (sampler != CPM_SAMPLER_GATHER && city->G > 0 && bucket_supported(N, city->ldc)) TRY(fleet_bucketize_async(fleet, N, ctx->aux_st));
     CU(cudaEventRecord(ctx->ev_aux[1], ctx->aux_st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev_aux[1], 0));
-    LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->st));   // main.jl:88
-    fleet->car_offset = 0; fleet->zone_valid = true; fleet->bucket_valid = false;
     cpm_day_opts o;
     memset(&o, 0, sizeof o);
     o.steps_per_hour = 1; o.sampler = sampler;
