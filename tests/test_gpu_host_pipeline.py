@@ -22,3 +22,39 @@ def test_host_pipeline_equals_two_step_path(ctx, N, cpz, density):
         got = sample_dataset_host(city, fleet, a, b, cars_per_zone=cpz, seed=9)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2] and got[3] == want[3]
     city.close(); fleet.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# error behaviour of the C ABI: int32 status + cpm_last_error(), no exceptions across the boundary
+# ---------------------------------------------------------------------------------------------------------
+def test_c_abi_reports_errors_by_status(ctx):
+    import ctypes as C
+    from carparkingmaps_b200 import City, CpmError, Fleet, Rng, _lib
+    lib = _lib.lib()
+    OK, ERR_ARG, ERR_STATE = 0, 1, 4
+    # NULL / nonsensical arguments: CPM_ERR_ARG and a message, nothing launched
+    out = C.c_void_p()
+    assert lib.cpm_city_create(ctx._h, 0, 24, C.byref(out)) == ERR_ARG and lib.cpm_last_error()
+    assert lib.cpm_city_create(ctx._h, 8, 0, C.byref(out)) == ERR_ARG
+    assert lib.cpm_fleet_create(ctx._h, 0, C.byref(out)) == ERR_ARG
+    assert lib.cpm_create_pdrive(ctx._h, None, None, 4, 24, 0.1, 0.9, 0.5, None) == ERR_ARG
+    # state errors: tables before inputs, a day before tables, p_dest that was not kept
+    city = City(ctx, 8, 24)
+    with pytest.raises(CpmError, match="inputs"):
+        city.build_pdrive(0.1, 0.9, 0.5)
+    dm, dist = synth_city(8, 24, seed=1, density=1.0)
+    city.upload(dm, dist)
+    fleet = Fleet(ctx, 80).init(10)
+    with pytest.raises(CpmError):
+        fleet.run_day(city, 3, with_time=False, rng=Rng(seed=1, stream=0))     # no p_drive / CDF yet
+    city.build_pdrive(0.1, 0.9, 0.5).build_pdestin(2, keep_p_dest=False)
+    with pytest.raises(CpmError, match="keep_p_dest"):
+        city.pdest()
+    # a fleet whose size does not match cars_per_zone * N
+    with pytest.raises(CpmError):
+        sample_dataset(city, fleet, cars_per_zone=11, seed=1)
+    # ... and the objects stay usable after every failure
+    fleet.run_day(city, 3, with_time=False, rng=Rng(seed=1, stream=0))
+    assert (fleet.counts()[0].sum(axis=0) == 80).all()
+    assert lib.cpm_ctx_sync(ctx._h) == OK
+    fleet.close(); city.close()
