@@ -371,7 +371,9 @@ static int32_t city_alloc_cdf(cpm_city *c)
     c->G = 0;
     if (c->N + 1 <= 65535) {                                       // guide entries are uint16
         int64_t g = 64;
-        while (g < (c->N + 3) / 4 && g < 8192) g *= 2;             // ~4 CDF entries per guide cell
+        // 4-8 CDF entries per guide cell.  Measured at cfg2 (profiles/README.md): G = 512 beats 1,024 (fewer 2-byte guide
+        // stores in the CDF build, 1 KB less per staged row) and 256 / 128 / 64 (more probes per search)
+        while (g < (c->N + 7) / 8 && g < 8192) g *= 2;
         c->G = (int32_t)g;
     }
     const int64_t guide_doubles = c->G ? ((int64_t)c->G + 1 + 7) / 8 * 2 : 0;   // (G+1) uint16 rounded up to 16 bytes
