@@ -37,7 +37,7 @@ PARAMS = dict(e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9)   # main.jl:37-40
 # dram__bytes_read.sum + dram__bytes_write.sum per k_bucket_sample launch, from the committed `ncu --set full` capture
 # (profiles/README.md); None where no capture exists
 REF_WALL_S = 150.0   # wall-clock target of a whole `--impl reference` run
-NCU_TRAFFIC_BYTES = {"cfg2": 118.5e6}   # profiles/r1_final_metrics_cfg2.summary.txt: mean over the 47 launches of one dataset pass
+NCU_TRAFFIC_BYTES = {"cfg2": 114.6e6}   # profiles/r1_final_metrics_cfg2.summary.txt: mean over the 47 launches of one dataset pass
 
 
 def measured_peak():
