@@ -84,6 +84,9 @@ struct cpm_ctx {
     cudaStream_t aux_st = nullptr;           // dataset pass: createpdrive runs beside the CDF build
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};   // fork (main -> aux), join (aux -> main)
     cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_hour;        // host-input pipeline: the std slab of hour t has landed
+    const cudaEvent_t *step_wait = nullptr;  // set around a resampling day: step s waits for step_wait[s / steps_per_hour]
+    int64_t n_step_wait = 0;
     std::vector<cudaEvent_t> ev;      // start0, stop0, start1, stop1, ...
     std::vector<int64_t> ev_launches; // step-kernel launches bracketed by each pair
 };
@@ -175,7 +178,7 @@ extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
     ctx->traj_state.release(); ctx->traj_trans.release(); ctx->tmp.release(); ctx->partials.release(); ctx->scalars.release();
     for (auto &b : ctx->u) b.release();
     if (ctx->aux_st) { cudaStreamSynchronize(ctx->aux_st); cudaStreamDestroy(ctx->aux_st); for (auto e : ctx->ev_aux) if (e) cudaEventDestroy(e); }
-    if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); for (auto e : ctx->ev_copy) if (e) cudaEventDestroy(e); }
+    if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); for (auto e : ctx->ev_copy) if (e) cudaEventDestroy(e); for (auto e : ctx->ev_hour) cudaEventDestroy(e); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->st);
     delete ctx;
     return CPM_OK;
@@ -632,6 +635,8 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
         a.parking = f->counts.as<uint32_t>() + (size_t)N * s;
         a.driving = f->counts.as<uint32_t>() + n_counts + (size_t)N * s;
         if (traj) { a.t_traj = s; a.write_next_state = (s + 1 < traj->T) ? 1 : 0; }
+        if (ctx->step_wait && o->with_time && s % o->steps_per_hour == 0 && a.hour < ctx->n_step_wait)
+            CU(cudaStreamWaitEvent(ctx->st, ctx->step_wait[a.hour], 0));   // this hour's std slab is still on its way up
         LAUNCH(ctx, launch_step_gather(a, ctx->st));
     }
     TRY(profile_close(ctx));
@@ -696,6 +701,8 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
         // events bracket the sampling kernel alone (the dominant kernel); every third launch only, so that the event
         // records do not perturb the back-to-back launch pipeline of the timed region (3 is coprime to 23, 24 and 47:
         // over a few days every hour is sampled equally often)
+        if (ctx->step_wait && o->with_time && s % o->steps_per_hour == 0 && a.hour < ctx->n_step_wait)
+            CU(cudaStreamWaitEvent(ctx->st, ctx->step_wait[a.hour], 0));   // this hour's std slab is still on its way up
         const bool timed = ctx->profiling && (ctx->prof_tick++ % 3 == 0);
         if (timed) TRY(profile_open(ctx, 1));
         LAUNCH(ctx, launch_bucket_sample(a, G, ctx->st));
@@ -806,10 +813,10 @@ static int32_t normalise_async(cpm_fleet *f, int64_t N, int64_t T, int64_t C_tot
 }
 
 // Enqueues main.jl:82-98 for one dataset on the context's stream (no host synchronisation): tables, fleet init, IVP,
-// resampling, normalisation.  `before_resampling` (nullable) is an event the resampling day waits for: the std slab of
+// resampling, normalisation.  `std_hour_events` (nullable): event t = the std slab of hour t is resident; the std slab of
 // datamatrix is only read there, so a host upload can still be in flight while the tables and the IVP run.
 static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cpm_params *pr, int64_t cars_per_zone,
-                                      uint64_t seed, int32_t sampler, cudaEvent_t before_resampling)
+                                      uint64_t seed, int32_t sampler, const cudaEvent_t *std_hour_events)
 {
     cpm_ctx *ctx = fleet->ctx;
     const int64_t N = city->N, T = city->T;
@@ -844,9 +851,12 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
         CU(cudaMemcpyAsync(fleet->lost_acc.p, &fleet->scalars.as<Scalars>()->lost, sizeof(unsigned long long),
                            cudaMemcpyDeviceToDevice, ctx->st));
     }
-    if (before_resampling) CU(cudaStreamWaitEvent(ctx->st, before_resampling, 0));
+    // host-input pipeline: the resampling step of hour t waits for the std slab of hour t only (the upload runs on)
+    ctx->step_wait = std_hour_events; ctx->n_step_wait = std_hour_events ? T : 0;
     o.n_steps = T; o.with_time = 1; o.rng.stream = 1;                                       // main.jl:95
-    TRY(run_day_async(city, fleet, &o, nullptr));
+    const int32_t rc_day = run_day_async(city, fleet, &o, nullptr);
+    ctx->step_wait = nullptr; ctx->n_step_wait = 0;
+    TRY(rc_day);
     TRY(normalise_async(fleet, N, T, fleet->C));                                            // saveresults.jl:6-28
     return CPM_OK;
 }
@@ -905,13 +915,23 @@ extern "C" int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, con
     CU(cudaMemcpyAsync(city->dist.p, distance_matrix_km, (size_t)city->N * city->N * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_st));
     CU(cudaMemcpyAsync(city->dm.p, datamatrix, slab, cudaMemcpyHostToDevice, ctx->copy_st));                       // means
     CU(cudaEventRecord(ctx->ev_copy[0], ctx->copy_st));
-    CU(cudaMemcpyAsync(city->dm.as<char>() + slab, reinterpret_cast<const char *>(datamatrix) + slab, slab,
-                       cudaMemcpyHostToDevice, ctx->copy_st));                                                       // stds
+    // stds, hour by hour, an event after each: the resampling step of hour t starts as soon as its slab is resident
+    while ((int64_t)ctx->ev_hour.size() < city->T) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_hour.push_back(e);
+    }
+    const size_t hour_bytes = (size_t)city->N * city->N * sizeof(double);
+    for (int64_t t = 0; t < city->T; ++t) {
+        CU(cudaMemcpyAsync(city->dm.as<char>() + slab + t * hour_bytes, reinterpret_cast<const char *>(datamatrix) + slab + t * hour_bytes,
+                           hour_bytes, cudaMemcpyHostToDevice, ctx->copy_st));
+        CU(cudaEventRecord(ctx->ev_hour[(size_t)t], ctx->copy_st));
+    }
     CU(cudaEventRecord(ctx->ev_copy[1], ctx->copy_st));
     city->have_inputs = true;
     city_invalidate(city);
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[0], 0));
-    int32_t rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, ctx->ev_copy[1]);
+    int32_t rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, ctx->ev_hour.data());
     if (rc != CPM_OK) { cudaStreamSynchronize(ctx->copy_st); cudaStreamSynchronize(ctx->st); return rc; }
     return sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);   // the caller may reuse its buffers after this
 }
