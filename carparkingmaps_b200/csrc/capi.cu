@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/cpm.h"
@@ -45,24 +46,60 @@ static int32_t fail(int32_t code, const char *fmt, const char *a = "", const cha
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
+// Device blocks are recycled: a released block goes to a per-device free list and the next ensure() takes the smallest
+// cached block that fits (and is not more than 2x too large) before it asks the driver.  A batch of cities of different
+// sizes (BASELINE configs[2]) otherwise spends most of its time in cudaMalloc / cudaFree of GB-sized tables.  All work
+// on a block is stream-ordered on the context's streams and every destroy synchronises first, so handing a block to its
+// next owner needs no further synchronisation.  The cache is emptied when an allocation fails and at cpm_ctx_destroy.
+struct BlockCache {
+    std::multimap<size_t, void *> free_blocks[16];
+    void *take(int dev, size_t bytes, size_t *cap)
+    {
+        auto &m = free_blocks[dev & 15];
+        auto it = m.lower_bound(bytes);
+        if (it == m.end() || it->first > 2 * bytes + (1u << 20)) return nullptr;
+        void *p = it->second;
+        *cap = it->first;
+        m.erase(it);
+        return p;
+    }
+    void give(int dev, void *p, size_t cap) { free_blocks[dev & 15].emplace(cap, p); }
+    void flush(int dev)
+    {
+        auto &m = free_blocks[dev & 15];
+        for (auto &kv : m) cudaFree(kv.second);
+        m.clear();
+    }
+};
+static BlockCache g_blocks;
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     int32_t ensure(size_t bytes)
     {
         if (bytes <= cap) return CPM_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (p) { cudaDeviceSynchronize(); release(); }   // growing: work in flight may still use the old block (cudaFree used to wait)
+        cudaGetDevice(&dev);
+        const size_t want = bytes ? bytes : 1;
+        if ((p = g_blocks.take(dev, want, &cap)) != nullptr) return CPM_OK;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {   // give the cached blocks back to the driver and try once more
+            cudaGetLastError();
+            g_blocks.flush(dev);
+            e = cudaMalloc(&p, want);
+        }
         if (e != cudaSuccess) {
-            p = nullptr;
+            p = nullptr; cap = 0;
             return fail(CPM_ERR_OOM, "cudaMalloc(%s bytes): %s", std::to_string(bytes).c_str(), cudaGetErrorString(e));
         }
-        cap = bytes;
+        cap = want;
         return CPM_OK;
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) g_blocks.give(dev, p, cap);
         p = nullptr; cap = 0;
     }
     template <typename T> T *as() const { return static_cast<T *>(p); }
@@ -180,6 +217,7 @@ extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
     if (ctx->aux_st) { cudaStreamSynchronize(ctx->aux_st); cudaStreamDestroy(ctx->aux_st); for (auto e : ctx->ev_aux) if (e) cudaEventDestroy(e); }
     if (ctx->copy_st) { cudaStreamSynchronize(ctx->copy_st); cudaStreamDestroy(ctx->copy_st); for (auto e : ctx->ev_copy) if (e) cudaEventDestroy(e); for (auto e : ctx->ev_hour) cudaEventDestroy(e); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->st);
+    g_blocks.flush(ctx->device);   // cached (unused) blocks go back to the driver
     delete ctx;
     return CPM_OK;
 }
