@@ -7,6 +7,7 @@
 #include <new>
 #include <string>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/cpm.h"
@@ -53,8 +54,10 @@ static int32_t fail(int32_t code, const char *fmt, const char *a = "", const cha
 // next owner needs no further synchronisation.  The cache is emptied when an allocation fails and at cpm_ctx_destroy.
 struct BlockCache {
     std::multimap<size_t, void *> free_blocks[16];
+    std::mutex mu;   // contexts of different host threads may share a device
     void *take(int dev, size_t bytes, size_t *cap)
     {
+        std::lock_guard<std::mutex> lock(mu);
         auto &m = free_blocks[dev & 15];
         auto it = m.lower_bound(bytes);
         if (it == m.end() || it->first > 2 * bytes + (1u << 20)) return nullptr;
@@ -63,9 +66,14 @@ struct BlockCache {
         m.erase(it);
         return p;
     }
-    void give(int dev, void *p, size_t cap) { free_blocks[dev & 15].emplace(cap, p); }
+    void give(int dev, void *p, size_t cap)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        free_blocks[dev & 15].emplace(cap, p);
+    }
     void flush(int dev)
     {
+        std::lock_guard<std::mutex> lock(mu);
         auto &m = free_blocks[dev & 15];
         for (auto &kv : m) cudaFree(kv.second);
         m.clear();
