@@ -223,7 +223,7 @@ def workload_config(args, N, cpz, T):
 def run_own(args, N, cpz, T, rank, world, local_rank):
     import torch
     import torch.distributed as dist_
-    from carparkingmaps_b200 import City, Context, Fleet, _lib, sample_dataset, sample_dataset_host
+    from carparkingmaps_b200 import City, Context, Fleet, _lib, sample_dataset, sample_dataset_host, sample_dataset_rows
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
@@ -312,8 +312,8 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             vals = [pinned(dm_F[ii, jj, tt, 0], np.float64), pinned(dm_F[ii, jj, tt, 1], np.float64)]
 
             def rows_step():
-                city.upload_rows(cols[0], cols[1], cols[2], vals[0], vals[1], dist_F)
-                return sample_dataset(city, fleet, **kw)
+                # one C-ABI call: ids, means and distances first, tables + IVP under the upload of the std column
+                return sample_dataset_rows(city, fleet, cols[0], cols[1], cols[2], vals[0], vals[1], dist_F, **kw)[:4]
 
             out_r = rows_step()
             assert np.array_equal(out_r[0], parking) and out_r[2] == A_drive, "row ingest changed the result"
@@ -327,7 +327,7 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             rows_ms = r0.elapsed_time(r1)
             e2e_rows = {"value": trans_per_step * e2e_steps / (rows_ms * 1e-3), "unit": "transitions/s",
                         "h2d_bytes_per_step": int(len(ii) * 28 + n_dist * 8), "rows": int(len(ii)), "ms_per_step": rows_ms / e2e_steps,
-                        "note": "pinned host columns (sourceid, dstid, hod, mean, std) scattered on the device"}
+                        "note": "pinned host columns (sourceid, dstid, hod, mean, std) through cpm_sample_dataset_rows: scattered on the device, the std column uploaded under the tables and the IVP"}
             for hnd in pins:
                 lib.cpm_host_free(hnd)
 

@@ -95,6 +95,8 @@ SIGNATURES = {
     "cpm_fleet_counts_device": (_i32, [_vp, _pp, C.POINTER(_i64)]),
     "cpm_sample_dataset": (_i32, [_vp, _vp, C.POINTER(CParams), _i64, _u64, _i32, _vp, _vp, C.POINTER(_d), C.POINTER(_i64)]),
     "cpm_sample_dataset_host": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(CParams), _i64, _u64, _i32, _vp, _vp, C.POINTER(_d), C.POINTER(_i64)]),
+    "cpm_sample_dataset_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(CParams), _i64, _u64, _i32, _vp, _vp,
+                                C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i64)]),
     "cpm_sweep": (_i32, [_vp, _vp, _i64, C.POINTER(CParams), _i64, _u64, _vp, _vp, _vp, _vp]),
 }
 

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -128,7 +129,7 @@ struct cpm_ctx {
     cudaStream_t copy_st = nullptr;          // host-input pipeline: uploads overlap the tables and the IVP
     cudaStream_t aux_st = nullptr;           // dataset pass: createpdrive runs beside the CDF build
     cudaEvent_t ev_aux[2] = {nullptr, nullptr};   // fork (main -> aux), join (aux -> main)
-    cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] first inputs, [1] all inputs, [2] compute -> copy, [3] distances
     std::vector<cudaEvent_t> ev_hour;        // host-input pipeline: the std slab of hour t has landed
     const cudaEvent_t *step_wait = nullptr;  // set around a resampling day: step s waits for step_wait[s / steps_per_hour]
     int64_t n_step_wait = 0;
@@ -862,7 +863,9 @@ static int32_t normalise_async(cpm_fleet *f, int64_t N, int64_t T, int64_t C_tot
 // resampling, normalisation.  `std_hour_events` (nullable): event t = the std slab of hour t is resident; the std slab of
 // datamatrix is only read there, so a host upload can still be in flight while the tables and the IVP run.
 static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cpm_params *pr, int64_t cars_per_zone,
-                                      uint64_t seed, int32_t sampler, const cudaEvent_t *std_hour_events)
+                                      uint64_t seed, int32_t sampler, const cudaEvent_t *std_hour_events,
+                                      const std::function<int32_t()> &before_resampling = nullptr,
+                                      cudaEvent_t dist_ready = nullptr)
 {
     cpm_ctx *ctx = fleet->ctx;
     const int64_t N = city->N, T = city->T;
@@ -879,6 +882,7 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     }
     TRY(city_build_pdestin_async(city, pr->e_dest, false, ctx->ev_aux[0]));                 // main.jl:85
     CU(cudaStreamWaitEvent(ctx->aux_st, ctx->ev_aux[0], 0));
+    if (dist_ready) CU(cudaStreamWaitEvent(ctx->aux_st, dist_ready, 0));   // row pipeline: the distances go up after the means
     TRY(city_build_pdrive_async(city, pr->p_min, pr->p_max, pr->e_drive, ctx->aux_st));     // main.jl:82
     // initializestates (main.jl:88) and the grouping of the cars by zone do not depend on the tables: second stream as well
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->aux_st));
@@ -897,6 +901,7 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
         CU(cudaMemcpyAsync(fleet->lost_acc.p, &fleet->scalars.as<Scalars>()->lost, sizeof(unsigned long long),
                            cudaMemcpyDeviceToDevice, ctx->st));
     }
+    if (before_resampling) TRY(before_resampling());   // row pipeline: the std column is scattered here
     // host-input pipeline: the resampling step of hour t waits for the std slab of hour t only (the upload runs on)
     ctx->step_wait = std_hour_events; ctx->n_step_wait = std_hour_events ? T : 0;
     o.n_steps = T; o.with_time = 1; o.rng.stream = 1;                                       // main.jl:95
@@ -953,6 +958,7 @@ extern "C" int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, con
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[1], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[2], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_copy[3], cudaEventDisableTiming));
     }
     const size_t slab = (size_t)city->N * city->N * city->T * sizeof(double);
     // the copy stream must not overwrite inputs that earlier work on the compute stream still reads
@@ -980,6 +986,68 @@ extern "C" int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, con
     int32_t rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, ctx->ev_hour.data());
     if (rc != CPM_OK) { cudaStreamSynchronize(ctx->copy_st); cudaStreamSynchronize(ctx->st); return rc; }
     return sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);   // the caller may reuse its buffers after this
+}
+
+// main.jl:74-98 for one dataset straight from the CSV columns, pipelined: the id columns, the means and the distances
+// go up first and are scattered (claims parked in the std slab); the tables and the IVP run while the std column is
+// still on its way; it is scattered just before the resampling day, the only consumer of standard deviations.
+extern "C" int32_t cpm_sample_dataset_rows(cpm_city *city, cpm_fleet *fleet, const int32_t *sourceid, const int32_t *dstid,
+                                           const int32_t *hod, const double *mean, const double *stddev, int64_t n_rows,
+                                           const double *distance_matrix_km, const cpm_params *pr, int64_t cars_per_zone,
+                                           uint64_t seed, int32_t sampler, double *parking, double *traffic, double *A_drive,
+                                           int64_t *n_lost, int64_t *n_skipped)
+{
+    ARG(city && fleet && distance_matrix_km && pr && cars_per_zone >= 1 && n_rows >= 0);
+    ARG(n_rows == 0 || (sourceid && dstid && hod && mean && stddev));
+    cpm_ctx *ctx = fleet->ctx;
+    ARG(city->ctx == ctx);
+    TRY(use(ctx));
+    TRY(city_alloc_inputs(city));
+    if (!ctx->copy_st) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_st, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev_copy) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const size_t nr = (size_t)n_rows;
+    const int64_t N = city->N, T = city->T;
+    TRY(ctx->tmp.ensure(nr * (3 * sizeof(int32_t) + 2 * sizeof(double)) + 64));
+    double *d_mean = ctx->tmp.as<double>();
+    double *d_sd = d_mean + nr;
+    int32_t *d_src = reinterpret_cast<int32_t *>(d_sd + nr), *d_dst = d_src + nr, *d_hod = d_dst + nr;
+    unsigned long long *d_bad = reinterpret_cast<unsigned long long *>(ctx->tmp.as<char>() + (nr * (3 * sizeof(int32_t) + 2 * sizeof(double)) + 7) / 8 * 8);
+    // the copy stream must not overwrite staging or inputs that earlier work on the compute stream still reads
+    CU(cudaEventRecord(ctx->ev_copy[2], ctx->st));
+    CU(cudaStreamWaitEvent(ctx->copy_st, ctx->ev_copy[2], 0));
+    if (nr) {
+        CU(cudaMemcpyAsync(d_src, sourceid, nr * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->copy_st));
+        CU(cudaMemcpyAsync(d_dst, dstid, nr * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->copy_st));
+        CU(cudaMemcpyAsync(d_hod, hod, nr * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->copy_st));
+        CU(cudaMemcpyAsync(d_mean, mean, nr * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_st));
+    }
+    CU(cudaEventRecord(ctx->ev_copy[0], ctx->copy_st));
+    // the distances are read by createpdrive only, which runs on the second stream after the two streaming passes of createpdestin
+    CU(cudaMemcpyAsync(city->dist.p, distance_matrix_km, (size_t)N * N * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_st));
+    CU(cudaEventRecord(ctx->ev_copy[3], ctx->copy_st));
+    if (nr) CU(cudaMemcpyAsync(d_sd, stddev, nr * sizeof(double), cudaMemcpyHostToDevice, ctx->copy_st));
+    CU(cudaEventRecord(ctx->ev_copy[1], ctx->copy_st));
+    // compute stream: zeros(N,N,T,2) (src/createdatamatrix.jl:7) while the columns travel, then the means
+    CU(cudaMemsetAsync(city->dm.p, 0, (size_t)N * N * T * 2 * sizeof(double), ctx->st));
+    CU(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->st));
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[0], 0));
+    LAUNCH(ctx, launch_rows_scatter_means(d_src, d_dst, d_hod, d_mean, n_rows, N, T, city->dm.as<double>(), d_bad, ctx->st));
+    city->have_inputs = true;
+    city_invalidate(city);
+    auto scatter_stds = [&]() -> int32_t {
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[1], 0));
+        LAUNCH(ctx, launch_rows_scatter_stds(d_src, d_dst, d_hod, d_sd, n_rows, N, T, city->dm.as<double>(), ctx->st));
+        return CPM_OK;
+    };
+    int32_t rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, nullptr, scatter_stds, ctx->ev_copy[3]);
+    if (rc != CPM_OK) { cudaStreamSynchronize(ctx->copy_st); cudaStreamSynchronize(ctx->st); return rc; }
+    unsigned long long bad = 0;
+    CU(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, ctx->st));
+    rc = sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);   // synchronises: host columns are free again
+    if (n_skipped) *n_skipped = (int64_t)bad;
+    return rc;
 }
 
 extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params, int64_t P,

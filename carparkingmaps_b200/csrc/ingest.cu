@@ -23,39 +23,64 @@ __device__ __forceinline__ int64_t row_cell(const int32_t *src, const int32_t *d
     return (i - 1) + N * ((j - 1) + N * (h - 1));
 }
 
+// claim_off / dst_off: element offsets of the slab a kernel claims in / writes to (0 = mean slab, N*N*T = std slab)
 __global__ void k_rows_claim(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, const int32_t *__restrict__ hod,
-                             int64_t n_rows, int64_t N, int64_t T, double *__restrict__ dm, unsigned long long *__restrict__ n_bad)
+                             int64_t n_rows, int64_t N, int64_t T, double *__restrict__ dm, int64_t claim_off,
+                             unsigned long long *__restrict__ n_bad)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = row_cell(src, dst, hod, r, N, T);
         if (c < 0) { atomicAdd(n_bad, 1ull); continue; }
-        atomicMax(reinterpret_cast<unsigned long long *>(dm) + c, (unsigned long long)(r + 1));
+        atomicMax(reinterpret_cast<unsigned long long *>(dm) + claim_off + c, (unsigned long long)(r + 1));
     }
 }
 
-template <int SLOT>   // 1: std slab, 0: mean slab (must run last: it overwrites the claim)
+// the row that holds the claim of its cell writes val[r] to the cell's slot in the slab at dst_off (the slab that holds
+// the claims must be written last: the value overwrites the claim)
 __global__ void k_rows_write(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, const int32_t *__restrict__ hod,
-                             const double *__restrict__ val, int64_t n_rows, int64_t N, int64_t T, double *__restrict__ dm)
+                             const double *__restrict__ val, int64_t n_rows, int64_t N, int64_t T, double *__restrict__ dm,
+                             int64_t claim_off, int64_t dst_off)
 {
-    const int64_t slab = N * N * T;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = row_cell(src, dst, hod, r, N, T);
         if (c < 0) continue;
-        if (reinterpret_cast<const unsigned long long *>(dm)[c] == (unsigned long long)(r + 1)) dm[c + SLOT * slab] = val[r];
+        if (reinterpret_cast<const unsigned long long *>(dm)[claim_off + c] == (unsigned long long)(r + 1)) dm[dst_off + c] = val[r];
     }
 }
 
 int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, const double *sd,
                         int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st)
 {
-    cudaMemsetAsync(dm, 0, (size_t)N * N * T * 2 * sizeof(double), st);   // zeros(number_zones, number_zones, T, 2), :7
+    const int64_t slab = N * N * T;
+    cudaMemsetAsync(dm, 0, (size_t)slab * 2 * sizeof(double), st);   // zeros(number_zones, number_zones, T, 2), :7
     cudaMemsetAsync(n_bad, 0, sizeof(unsigned long long), st);
     if (n_rows <= 0) return 0;
     const int g = sampler_grid(n_rows);
-    k_rows_claim<<<g, 256, 0, st>>>(src, dst, hod, n_rows, N, T, dm, n_bad);
-    k_rows_write<1><<<g, 256, 0, st>>>(src, dst, hod, sd, n_rows, N, T, dm);
-    k_rows_write<0><<<g, 256, 0, st>>>(src, dst, hod, mean, n_rows, N, T, dm);
+    k_rows_claim<<<g, 256, 0, st>>>(src, dst, hod, n_rows, N, T, dm, 0, n_bad);          // claims live in the mean slab
+    k_rows_write<<<g, 256, 0, st>>>(src, dst, hod, sd, n_rows, N, T, dm, 0, slab);
+    k_rows_write<<<g, 256, 0, st>>>(src, dst, hod, mean, n_rows, N, T, dm, 0, 0);
     return 3;
+}
+
+// The same scatter in two halves for the pipelined dataset pass: the means first (claims parked in the std slab, which
+// nothing reads before the resampling day), the standard deviations later, when their column has arrived.
+int launch_rows_scatter_means(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, int64_t n_rows,
+                              int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st)
+{
+    const int64_t slab = N * N * T;
+    if (n_rows <= 0) return 0;
+    const int g = sampler_grid(n_rows);
+    k_rows_claim<<<g, 256, 0, st>>>(src, dst, hod, n_rows, N, T, dm, slab, n_bad);
+    k_rows_write<<<g, 256, 0, st>>>(src, dst, hod, mean, n_rows, N, T, dm, slab, 0);
+    return 2;
+}
+int launch_rows_scatter_stds(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *sd, int64_t n_rows,
+                             int64_t N, int64_t T, double *dm, cudaStream_t st)
+{
+    const int64_t slab = N * N * T;
+    if (n_rows <= 0) return 0;
+    k_rows_write<<<sampler_grid(n_rows), 256, 0, st>>>(src, dst, hod, sd, n_rows, N, T, dm, slab, slab);
+    return 1;
 }
 
 // Centroid distance matrix -- src/processgeodata.jl:150-166: equirectangular formula with the reference's

@@ -114,6 +114,11 @@ int launch_normalise_counts(const uint32_t *parking, const uint32_t *driving, in
 int launch_rows_scatter(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, const double *sd,
                         int64_t n_rows, int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st);
 
+int launch_rows_scatter_means(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *mean, int64_t n_rows,
+                              int64_t N, int64_t T, double *dm, unsigned long long *n_bad, cudaStream_t st);
+int launch_rows_scatter_stds(const int32_t *src, const int32_t *dst, const int32_t *hod, const double *sd, int64_t n_rows,
+                             int64_t N, int64_t T, double *dm, cudaStream_t st);
+
 int launch_distance_matrix(const double *lat, const double *lon, int64_t N, double *out, cudaStream_t st);
 int launch_polygon_centroids(double *lon, double *lat, int64_t N, int64_t V, double *c_lat, double *c_lon, double *area, cudaStream_t st);
 

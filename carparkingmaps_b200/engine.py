@@ -265,6 +265,25 @@ def sample_dataset_host(city: City, fleet: Fleet, datamatrix, distance_matrix_km
     return parking, traffic, A.value, lost.value
 
 
+def sample_dataset_rows(city: City, fleet: Fleet, sourceid, dstid, hod, mean, stddev, distance_matrix_km, *, e_drive=0.5, e_dest=2,
+                        p_min=0.1, p_max=0.9, cars_per_zone=1000, seed=0, sampler=L.SAMPLER_AUTO, want_parking=True):
+    """main.jl:74-98 for one dataset from the CSV columns (createdatamatrix on the device, src/createdatamatrix.jl:8-23),
+    the upload pipelined with the computation.  Returns (parking[N,T], traffic[T], A_drive, n_lost, n_skipped_rows)."""
+    cols = [np.ascontiguousarray(a, dtype=np.int32) for a in (sourceid, dstid, hod)]
+    vals = [np.ascontiguousarray(a, dtype=np.float64) for a in (mean, stddev)]
+    n = cols[0].shape[0]
+    assert all(a.shape == (n,) for a in cols + vals)
+    dist = _f64F(distance_matrix_km, (city.N, city.N))
+    pr = L.CParams(float(e_drive), float(e_dest), float(p_min), float(p_max))
+    parking = np.empty((city.N, city.T), order="F") if want_parking else None
+    traffic = np.empty(city.T)
+    A, lost, skipped = C.c_double(), C.c_int64(), C.c_int64()
+    L.check(L.lib().cpm_sample_dataset_rows(city._h, fleet._h, _ptr(cols[0]), _ptr(cols[1]), _ptr(cols[2]), _ptr(vals[0]), _ptr(vals[1]), n,
+                                            _ptr(dist), C.byref(pr), int(cars_per_zone), int(seed), sampler, _ptr(parking),
+                                            _ptr(traffic), C.byref(A), C.byref(lost), C.byref(skipped)))
+    return parking, traffic, A.value, lost.value, skipped.value
+
+
 def sweep(city: City, initial_zones, params, *, seed=0, common_random_numbers=False, want_parking=False, streams=None):
     """Model-selection sweep over P parameter sets (rows of `params`: e_drive, e_dest, p_min, p_max).
     `streams`: Philox stream id per set (default 2 + p; all equal with common_random_numbers).

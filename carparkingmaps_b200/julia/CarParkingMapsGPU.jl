@@ -19,7 +19,8 @@
 module CarParkingMapsGPU
 
 export createpdrive, createpdestin, initializestates, solveinitialvalueproblem, resampling,
-       averagedrivingtime, correctparameters, zonehistogram, sampledataset, polygoncentroids, distancematrix, cpm_seed!
+       averagedrivingtime, correctparameters, zonehistogram, sampledataset, sampledatasetrows, polygoncentroids,
+       distancematrix, cpm_seed!
 
 const LIBCPM = get(ENV, "LIBCPM", joinpath(@__DIR__, "..", "libcpm.so"))
 
@@ -195,6 +196,32 @@ function sampledataset(datamatrix::Array{Float64,4}, distance_matrix_km::Array{F
         ccall((:cpm_fleet_destroy, LIBCPM), Int32, (Ptr{Cvoid},), fleet[])
         ccall((:cpm_city_destroy, LIBCPM), Int32, (Ptr{Cvoid},), city[])
     end
+    return parking, traffic, A[], lost[]
+end
+
+# the same from the rows of the travel-time CSV (the columns createdatamatrix reads, src/createdatamatrix.jl:8-23): no dense
+# datamatrix on the host at all, ~9x less PCIe traffic for Melbourne-like data
+function sampledatasetrows(sourceid::Vector{Int32}, dstid::Vector{Int32}, hod::Vector{Int32}, mean_travel_time::Vector{Float64},
+                           standard_deviation_travel_time::Vector{Float64}, distance_matrix_km::Array{Float64,2}, number_zones;
+                           seed::Integer = SEED[])
+    N, T = Int64(number_zones), Int64(g(:T))
+    cpz = Int64(g(:cars_per_zone))
+    city, fleet = Ref{Ptr{Cvoid}}(C_NULL), Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cpm_city_create, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx(), N, T, city))
+    check(ccall((:cpm_fleet_create, LIBCPM), Int32, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx(), N * cpz, fleet))
+    parking, traffic, A, lost, skipped = zeros(N, T), zeros(1, T), Ref{Float64}(0.0), Ref{Int64}(0), Ref{Int64}(0)
+    try
+        pr = CpmParams(Float64(g(:e_drive)), Float64(g(:e_dest)), Float64(g(:p_min)), Float64(g(:p_max)))
+        check(ccall((:cpm_sample_dataset_rows, LIBCPM), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64},
+                     Ref{CpmParams}, Int64, UInt64, Int32, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}, Ref{Int64}),
+                    city[], fleet[], sourceid, dstid, hod, mean_travel_time, standard_deviation_travel_time, Int64(length(sourceid)),
+                    distance_matrix_km, Ref(pr), cpz, UInt64(seed), Int32(0), parking, traffic, A, lost, skipped))
+    finally
+        ccall((:cpm_fleet_destroy, LIBCPM), Int32, (Ptr{Cvoid},), fleet[])
+        ccall((:cpm_city_destroy, LIBCPM), Int32, (Ptr{Cvoid},), city[])
+    end
+    skipped[] > 0 && @warn "rows outside the matrix were skipped (reference: BoundsError)" rows = skipped[]
     return parking, traffic, A[], lost[]
 end
 

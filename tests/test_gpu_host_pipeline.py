@@ -3,7 +3,7 @@ upload + sample_dataset returns, also when called back to back on the same handl
 import numpy as np
 import pytest
 
-from carparkingmaps_b200 import City, Fleet, sample_dataset, sample_dataset_host
+from carparkingmaps_b200 import City, Fleet, sample_dataset, sample_dataset_host, sample_dataset_rows
 from carparkingmaps_b200.synth import synth_city
 
 pytestmark = pytest.mark.gpu
@@ -22,6 +22,43 @@ def test_host_pipeline_equals_two_step_path(ctx, N, cpz, density):
         got = sample_dataset_host(city, fleet, a, b, cars_per_zone=cpz, seed=9)
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and got[2] == want[2] and got[3] == want[3]
     city.close(); fleet.close()
+
+
+@pytest.mark.parametrize("N,cpz,density", [(64, 100, 0.3), (130, 40, 0.09), (33, 50, 1.0)])
+def test_row_pipeline_equals_two_step_path(ctx, N, cpz, density):
+    """cpm_sample_dataset_rows (ids + means first, tables and IVP under the upload of the std column, stds scattered
+    before the resampling day) == cpm_city_upload_rows + cpm_sample_dataset, including duplicate keys (last row wins),
+    the 0 -> N / hour 0 -> 24 remaps and rows outside the matrix."""
+    T = 24
+    dm, dist = synth_city(N, T, seed=N, density=density)
+    ii, jj, tt = np.nonzero(dm[:, :, :, 0])
+    rs = np.random.default_rng(N)
+    order = rs.permutation(len(ii))
+    ii, jj, tt = ii[order], jj[order], tt[order]
+    src, dst, hod = ((ii + 1) % N).astype(np.int32), ((jj + 1) % N).astype(np.int32), ((tt + 1) % 24).astype(np.int32)
+    mean, sd = dm[ii, jj, tt, 0].copy(), dm[ii, jj, tt, 1].copy()
+    # duplicates that must lose (they come first), and rows outside the matrix
+    dup = rs.integers(0, len(ii), 50)
+    src = np.concatenate([src[dup], src, np.array([N + 3, 1], np.int32)])
+    dst = np.concatenate([dst[dup], dst, np.array([1, -2], np.int32)])
+    hod = np.concatenate([hod[dup], hod, np.array([5, 5], np.int32)])
+    mean = np.concatenate([mean[dup] + 17.0, mean, [100.0, 100.0]])
+    sd = np.concatenate([sd[dup] + 3.0, sd, [1.0, 1.0]])
+    city, fleet = City(ctx, N, T), Fleet(ctx, N * cpz)
+    assert city.upload_rows(src, dst, hod, mean, sd, dist) == 2
+    want = sample_dataset(city, fleet, cars_per_zone=cpz, seed=9)
+    got_dm, _ = city.download_inputs()
+    np.testing.assert_array_equal(got_dm, dm)
+    city2, fleet2 = City(ctx, N, T), Fleet(ctx, N * cpz)
+    for _ in range(2):   # twice: the second call reuses staging and inputs of the first
+        got = sample_dataset_rows(city2, fleet2, src, dst, hod, mean, sd, dist, cars_per_zone=cpz, seed=9)
+        assert got[4] == 2
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        assert got[2] == want[2] and got[3] == want[3]
+    np.testing.assert_array_equal(city2.download_inputs()[0], dm)          # the std slab no longer holds claims
+    for o in (city, fleet, city2, fleet2):
+        o.close()
 
 
 # ---------------------------------------------------------------------------------------------------------
