@@ -61,6 +61,20 @@ def test_row_pipeline_equals_two_step_path(ctx, N, cpz, density):
         o.close()
 
 
+def test_row_pipeline_without_rows(ctx):
+    """An empty CSV: the datamatrix is all zeros, p_drive is zero everywhere (src/createpdrive.jl:28: NaN max_t), nobody drives."""
+    N, cpz, T = 12, 30, 24
+    _, dist = synth_city(N, T, seed=3, density=1.0)
+    e32, e64 = np.zeros(0, np.int32), np.zeros(0)
+    city, fleet = City(ctx, N, T), Fleet(ctx, N * cpz)
+    parking, traffic, A, lost, skipped = sample_dataset_rows(city, fleet, e32, e32, e32, e64, e64, dist, cars_per_zone=cpz, seed=1)
+    assert skipped == 0 and lost == 0 and A == 0.0
+    np.testing.assert_array_equal(parking, np.full((N, T), 1.0 / N))      # every car stays in its zone
+    assert np.isnan(traffic).all()                                         # (0 - 0) / (0 - 0), src/saveresults.jl:26
+    assert not city.download_inputs()[0].any()
+    city.close(); fleet.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # error behaviour of the C ABI: int32 status + cpm_last_error(), no exceptions across the boundary (SURVEY 8b)
 # ---------------------------------------------------------------------------------------------------------
