@@ -83,6 +83,7 @@ SIGNATURES = {
     "cpm_city_get_pdrive": (_i32, [_vp, _vp]),
     "cpm_city_get_pdest": (_i32, [_vp, _vp]),
     "cpm_city_get_cdf": (_i32, [_vp, _vp]),
+    "cpm_city_get_guide": (_i32, [_vp, _i64, _vp, C.POINTER(_i32)]),
     "cpm_fleet_create": (_i32, [_vp, _i64, _pp]),
     "cpm_fleet_destroy": (_i32, [_vp]),
     "cpm_fleet_init": (_i32, [_vp, _i64, _i64]),

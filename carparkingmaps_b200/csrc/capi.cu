@@ -533,6 +533,21 @@ extern "C" int32_t cpm_city_get_cdf(cpm_city *c, double *out)
     return CPM_OK;
 }
 
+extern "C" int32_t cpm_city_get_guide(cpm_city *c, int64_t hour, uint16_t *guide_out, int32_t *G_out)
+{
+    ARG(c && G_out && hour >= 0 && hour < c->T);
+    TRY(use(c->ctx));
+    if (!c->have_cdf) return fail(CPM_ERR_STATE, "the CDF has not been built");
+    *G_out = c->G;
+    if (c->G == 0 || !guide_out) return CPM_OK;
+    // the guide of a row sits behind its N running sums (offset goff doubles inside the row block of ldc doubles)
+    const char *src = c->cdf.as<char>() + ((size_t)hour * c->N * c->ldc + (size_t)c->goff) * sizeof(double);
+    CU(cudaMemcpy2DAsync(guide_out, (size_t)(c->G + 1) * sizeof(uint16_t), src, (size_t)c->ldc * sizeof(double),
+                         (size_t)(c->G + 1) * sizeof(uint16_t), (size_t)c->N, cudaMemcpyDeviceToHost, c->ctx->st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    return CPM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // fleet
 // ------------------------------------------------------------------------------------------------

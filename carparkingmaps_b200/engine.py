@@ -172,6 +172,16 @@ class City:
         L.check(L.lib().cpm_city_get_cdf(self._h, _ptr(out)))
         return out
 
+    def guide(self, hour: int):
+        """Guide tables of one table hour: uint16 [N, G+1], guide[o, b] = #{j : cdf[o, j] < b/G} (None without a guide)."""
+        G = C.c_int32()
+        L.check(L.lib().cpm_city_get_guide(self._h, int(hour), None, C.byref(G)))
+        if G.value == 0:
+            return None
+        out = np.empty((self.N, G.value + 1), dtype=np.uint16)
+        L.check(L.lib().cpm_city_get_guide(self._h, int(hour), _ptr(out), C.byref(G)))
+        return out
+
     def close(self):
         if self._h:
             L.lib().cpm_city_destroy(self._h)

@@ -179,6 +179,10 @@ int32_t cpm_city_get_pdrive(cpm_city *city, double *p_drive_out);
 int32_t cpm_city_get_pdest(cpm_city *city, double *p_dest_out);       /* needs keep_p_dest */
 /* sampling CDF rows: [T][N origins][N destinations], destination fastest */
 int32_t cpm_city_get_cdf(cpm_city *city, double *cdf_out);
+/* the guide ("cut-point") tables of one table hour: guide_out [N origins][G+1] uint16, guide[b] = #{j : cdf[j] < b/G};
+ * the categorical draw of src/resampling.jl:38-45 starts its search at guide[floor(u*G)].  G_out = 0: this city has no
+ * guide (more than 65,534 zones).  guide_out may be NULL to query G only. */
+int32_t cpm_city_get_guide(cpm_city *city, int64_t hour, uint16_t *guide_out, int32_t *G_out);
 
 int32_t cpm_fleet_create(cpm_ctx *ctx, int64_t C, cpm_fleet **out);
 int32_t cpm_fleet_destroy(cpm_fleet *fleet);
