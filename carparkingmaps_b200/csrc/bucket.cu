@@ -1,332 +1,311 @@
-// bucket.cu -- the "bucket" sampler: cars are kept grouped by their current zone, so that a CTA works on one
-// zone at a time with the origin's fp64 CDF row (and its guide table) staged in shared memory by a TMA bulk copy
-// (cp.async.bulk + mbarrier).
+// bucket.cu -- the "bucket" sampler: cars are kept grouped by their current zone, so that the categorical draw of a car
+// probes its origin's fp64 CDF row (and guide table) in SHARED memory, staged there by TMA bulk copies
+// (cp.async.bulk + mbarrier) through a ring of row buffers.
 //
-// Why (profiles/README.md r1a): with one thread per car in car-id order the categorical draw is a chain of
-// dependent L2/HBM loads under divergence; grouping by origin turns it into shared-memory probes, reads every CDF
-// row once per step (the algorithmic table traffic), and makes the per-zone parked-car histogram free
-// (it IS the bucket size).  Results are identical to the gather sampler and to the reference algorithm because
-// every draw is keyed by (global car id, step), not by processing order.
+// Why grouped (profiles/README.md r1a): with one thread per car in car-id order the draw is a chain of dependent,
+// fully divergent L2/HBM loads; grouping by origin reads every CDF row once per step (the algorithmic table traffic,
+// SURVEY 8d), turns the probes into shared-memory reads and makes the parked-car histogram free (it IS the bucket
+// size).  Results are identical to the gather sampler and to the reference algorithm because every draw is keyed by
+// (global car id, step), not by processing order.
 //
-// One step is a counting sort by destination zone with per-CTA histograms (no global atomics on the data path):
-//   k_bucket_sample   CTA g owns a fixed slab of slots [g*S, (g+1)*S); it walks the zone segments inside its slab,
-//                     does phases 1-3 of the reference step per car, ranks every car among the cars OF THIS CTA
-//                     with the same destination (shared-memory histogram), writes (destination, rank) per slot
-//                     and finally its histogram row M[g][*]
-//   k_bucket_colscan  exclusive prefix of M over g per destination (-> where CTA g's cars start inside each
-//                     destination bucket) and the new bucket sizes (= parked cars per zone at the next step)
-//   k_bucket_scatter  prefix sum of the new bucket sizes, then perm_next[start[dest] + M[g][dest] + rank] = car
+// One step is a counting sort by destination zone, two kernels chained by programmatic dependent launch:
+//   k_bucket_sample   one fat CTA per SM owns a fixed slab of slots.  Its warps walk the zone segments of the slab
+//                     independently of each other (no block barrier inside the walk): per 32*U slots a warp does
+//                     phases 1-3 of the reference step, ranks every car among the cars OF THIS CTA with the same
+//                     destination (shared-memory histogram) and writes (destination, rank) per slot.  The warp that
+//                     finishes a zone last re-arms the zone's ring buffer with the row R zones ahead.  The CTA ends
+//                     with ONE global atomicAdd per destination it saw: the return value is where its cars start
+//                     inside that destination's bucket (the order of cars inside a bucket is irrelevant to the
+//                     results), the padded counters end up as the new bucket sizes.
+//   k_bucket_scatter  CTA g re-reads slab g, sorts it by destination in shared memory (a 4-byte shared store per car),
+//                     then writes it out: consecutive threads hold consecutive cars of one destination, so the global
+//                     stores are runs instead of one 32-byte sector per car (profiles/r2: 16.7 -> ~7 us).  Every CTA
+//                     derives the next bucket starts from the padded counters (block 0 publishes them, with the compact
+//                     histogram copy); CTA g also notes which zone its slab starts in at the next step.
+// Round 1's design (per-CTA histogram rows for 592 CTAs + a column-scan kernel + a sector-per-car scatter, block
+// barriers around a compaction list) is in the history of this file; see profiles/README.md for the measurements.
 // Reference semantics: src/resampling.jl:11-83, src/solveinitialvalueproblem.jl:11-53, src/saveresults.jl:8-17.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "async.cuh"
 
 namespace cpm {
 
-// Programmatic dependent launch: the three kernels of a step are launched with programmatic stream serialization, so
-// the next kernel's CTAs are scheduled (and run their shared-memory prologue) while the previous kernel drains;
+// Programmatic dependent launch: the kernels of a step are launched with programmatic stream serialization, so the
+// next kernel's CTAs are scheduled (and run their shared-memory prologue) while the previous kernel drains;
 // pdl_wait() blocks until the previous kernel has completed and its writes are visible.  Every global access of these
 // kernels comes after pdl_wait().  Both are no-ops for a plain launch.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// ------------------------------------------------------------------------------------------------
-// shared-memory layout of k_bucket_sample
-// ------------------------------------------------------------------------------------------------
-struct SampleSmem {
-    double *row;          // [ldc]   the origin's CDF row + guide table (TMA destination)
-    double *srch_u;       // [CH]    u_dest of the compacted drivers
-    uint32_t *hist;       // [N+1]   cars of this CTA per destination bin (never cleared inside a launch)
-    uint16_t *srch_idx;   // [CH]    chunk-relative slot of each compacted driver
-    uint64_t *bar;
-    uint32_t *misc;       // [0],[1] n_search ping-pong counters, [2] scratch of the zone search
-};
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kMaxRing = 8;
+constexpr size_t kSmemCap = 227 * 1024;
+constexpr size_t kSampleTail = 128;      // mbarriers, ring counters, reduction scratch
 
 __host__ __device__ inline size_t hist_bytes(int64_t N) { return ((size_t)(N + 1) * 4 + 15) / 16 * 16; }
-__host__ __device__ inline size_t sample_smem_bytes(int64_t N, int64_t ldc, int CH)
-{
-    return (size_t)ldc * 8 + (size_t)CH * 8 + hist_bytes(N) + (size_t)CH * 2 + 64;
-}
-
-__device__ __forceinline__ SampleSmem carve(unsigned char *p, int64_t N, int64_t ldc, int CH)
-{
-    SampleSmem s;
-    s.row = reinterpret_cast<double *>(p); p += (size_t)ldc * 8;
-    s.srch_u = reinterpret_cast<double *>(p); p += (size_t)CH * 8;
-    s.hist = reinterpret_cast<uint32_t *>(p); p += hist_bytes(N);
-    s.srch_idx = reinterpret_cast<uint16_t *>(p); p += (size_t)CH * 2;
-    s.bar = reinterpret_cast<uint64_t *>(p); p += 16;
-    s.misc = reinterpret_cast<uint32_t *>(p);
-    return s;
-}
-
-// largest z in [0, nb) with start[z] <= x  (start is non-decreasing, start[0] = 0, start[nb] = C > x)
-__device__ __forceinline__ int zone_of_slot(const uint32_t *__restrict__ start, int nb, uint32_t x)
-{
-    int lo = 0, hi = nb;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(start + mid) <= x) lo = mid; else hi = mid;
-    }
-    return lo;
-}
 
 // ------------------------------------------------------------------------------------------------
 // k_bucket_sample
 // ------------------------------------------------------------------------------------------------
-template <int THREADS, int CH, bool INJ>   // INJ: uniform variates injected by the caller (parity tests) instead of Philox
-__global__ void __launch_bounds__(THREADS) k_bucket_sample(const BucketArgs a)
+// Philox4x32-10 words of (car, step, phase); u52() of (o0,o1) and (o2,o3) are the two uniforms of philox_pair()
+__device__ __forceinline__ void philox_words(const RngDev &r, int64_t car, uint32_t step, uint32_t phase, uint32_t (&o)[4])
+{
+    const uint64_t g = (uint64_t)(r.car_offset + car);
+    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), step, r.stream * 2u + phase, r.k0, r.k1, o);
+}
+
+template <int THREADS, int U, bool INJ, bool TIME>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const BucketArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int R = CH / THREADS;
+    constexpr int W = THREADS / 32, GS = 32 * U;
     const int64_t N = a.N, NN = a.N * a.N;
     const int Ni = (int)N, NB = Ni + 1;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    SampleSmem s = carve(smem_raw, N, a.ldc, CH);
-    const uint32_t row_bytes = (uint32_t)(a.ldc * 8);   // CDF row + its guide table in one bulk copy
-    const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
-    const double *__restrict__ pd_t = a.p_drive + N * a.hour;
-    const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
-    constexpr bool inj = INJ;
-    const int64_t uoff = a.rng.ld * a.step;
-    uint32_t *const hist = s.hist;
+    const int R = a.ring;
+    const uint32_t row_bytes = (uint32_t)(a.ldc * 8);   // CDF row + its guide table: one bulk copy
+    double *const ring = reinterpret_cast<double *>(smem_raw);
+    uint32_t *const hist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)R * row_bytes);   // [N+1] cars of this CTA per destination
+    uint64_t *const full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(hist) + hist_bytes(N));   // [kMaxRing]
+    uint32_t *const done = reinterpret_cast<uint32_t *>(full + kMaxRing);                                         // [kMaxRing]
+    unsigned long long *const red = reinterpret_cast<unsigned long long *>(done + kMaxRing);                      // [2]
 
-    if (tid == 0) { mbar_init(&s.bar[0], 1); fence_mbar_init(); }
+    if (tid == 0) {
+        for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    if (tid < kMaxRing) done[tid] = 0u;
+    if (tid < 2) red[tid] = 0ull;
     for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(hist)[x] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid < 3) s.misc[tid] = 0u;
     __syncthreads();
     pdl_trigger();
     pdl_wait();
 
-    uint32_t par = 0u;
-    unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
+    const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
+    const double *__restrict__ pd_t = a.p_drive + N * a.hour;
+    const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
+    const int64_t uoff = a.rng.ld * a.step;
     const uint64_t l2_stream = l2_evict_first_policy();
-    int pp = 0;   // which n_search counter the current chunk uses
+    unsigned long long t_hi = 0ull, t_lo = 0ull;
 
     // this CTA's slab of slots
     const uint32_t slab_lo = (uint32_t)min((int64_t)blockIdx.x * a.slab, a.C);
     const uint32_t slab_hi = (uint32_t)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
-    uint32_t pos = slab_lo;
-    // pull the slab's car ids towards L2 now (one 128-byte line per thread and trip); they are read chunk by chunk below
-    for (uint32_t x = slab_lo + (uint32_t)tid * 32u; x < slab_hi; x += THREADS * 32u)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.perm_cur + x));
-    // the slab's first zone, z = #{b : start[b] <= slab_lo} - 1, by one coalesced pass over the bucket starts (a binary
-    // search would be a chain of ~12 dependent L2 loads at the head of every CTA).  Shared memory is NOT used to stage
-    // the starts: the L1 it would take is worth more to the travel-time gathers of the resampling steps.
-    {
-        unsigned below = 0;
-        for (int x = tid; x < NB; x += THREADS) below += (__ldg(a.start + x) <= slab_lo) ? 1u : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-        if (lane == 0 && below) atomicAdd(&s.misc[2], below);
-    }
-    __syncthreads();
-    int z = (slab_lo < slab_hi) ? (int)s.misc[2] - 1 : NB;
 
-    while (pos < slab_hi) {
-        // zone segment [pos, seg_end) of bin z inside the slab; skip empty zones (usually none)
-        uint32_t z_end = __ldg(a.start + z + 1);
-        while (z_end <= pos) z_end = __ldg(a.start + (++z) + 1);   // start[NB] = C > pos: terminates
-        const uint32_t seg_end = min(z_end, slab_hi);
-        const int bin = z;
-        const bool is_zone = bin < Ni;
-        const double pd = is_zone ? __ldg(pd_t + bin) : -1.0;
-        const bool rowzero = is_zone ? (rz_t[bin] != 0) : true;
-        const bool need_row = is_zone && !rowzero;
-        unsigned nd_warp = 0;
+    // (re-)arm ring buffer `slot` for bin z: a TMA row copy when cars of the slab may search it, a plain arrival otherwise
+    auto issue = [&](int z, int slot) {
+        const uint32_t lo = max(__ldg(a.start + z), slab_lo), hi = min(__ldg(a.start + z + 1), slab_hi);
+        if (z < Ni && lo < hi && rz_t[z] == 0) {
+            fence_proxy_async();   // the buffer's last readers signalled `done` before this
+            mbar_expect_tx(&full[slot], row_bytes);
+            tma_bulk_g2s(ring + (size_t)slot * a.ldc, cdf_t + (int64_t)z * a.ldc, row_bytes, &full[slot], l2_stream);
+        } else mbar_arrive(&full[slot]);
+    };
 
-        for (uint32_t lo = pos; lo < seg_end; lo += CH) {
-            const int n = (int)min((uint32_t)CH, seg_end - lo);
-            const bool first_chunk = lo == pos;
-            if (need_row && first_chunk && tid == 0) {   // the row buffer's last readers passed the barrier that ended phase B
-                fence_proxy_async();
-                mbar_expect_tx(&s.bar[0], row_bytes);
-                tma_bulk_g2s(s.row, cdf_t + (int64_t)bin * a.ldc, row_bytes, &s.bar[0], l2_stream);
+    if (slab_lo < slab_hi) {
+        const int z0 = (int)__ldg(a.first_zone + blockIdx.x);   // the bin that holds slot slab_lo
+        if (tid == 0)
+            for (int k = 0; k < R; ++k) {
+                const int z = z0 + k;
+                if (z >= NB || __ldg(a.start + z) >= slab_hi) break;
+                issue(z, k);
             }
-            const int32_t *__restrict__ perm = a.perm_cur + lo;
-            uint32_t *__restrict__ out = a.dr + lo;
-            uint32_t *const n_search_ctr = &s.misc[pp];
-
-            // ---- phase A: Bernoulli drive decision for every car of the chunk (src/resampling.jl:11-22) ----
-            int32_t ids[R];
+        uint32_t rot = 0;   // groups handed out so far: group j of a zone goes to warp (rot + j) % W
+        int slot = 0;       // ring buffer of bin z0 + k: k % R, in its (k / R)-th use
+        uint32_t phase = 0u;
+        for (int k = 0;; ++k, ++slot) {
+            const int z = z0 + k;
+            if (z >= NB) break;
+            if (slot == R) { slot = 0; phase ^= 1u; }
+            const uint32_t zs = __ldg(a.start + z);
+            if (zs >= slab_hi) break;
+            const uint32_t lo = max(zs, slab_lo), hi = min(__ldg(a.start + z + 1), slab_hi);
+            mbar_wait(&full[slot], phase);   // every lane observes the completion of the row copy
+            if (lo < hi) {
+                const bool is_zone = z < Ni;
+                const double pd = is_zone ? __ldg(pd_t + z) : -1.0;
+                const bool rowzero = is_zone ? (rz_t[z] != 0) : true;
+                const double *row = ring + (size_t)slot * a.ldc;
+                const uint16_t *gd = reinterpret_cast<const uint16_t *>(row + a.goff);
+                const uint32_t ngroups = (hi - lo + GS - 1) / GS;
+                unsigned nd_warp = 0;
+                for (uint32_t j = (uint32_t)(warp + W - (int)(rot % W)) % W; j < ngroups; j += W) {
+                    const uint32_t x = lo + j * GS + lane;
+                    // ---- phase 1: Bernoulli drive decision (src/resampling.jl:11-22) ----
+                    int32_t id[U];
+                    double u2[U];
+                    uint32_t cell[U], m_stay[U];
+                    bool act[U], srch[U], stay[U];
 #pragma unroll
-            for (int r = 0; r < R; ++r) { const int k = r * THREADS + tid; ids[r] = (is_zone && k < n) ? __ldg(perm + k) : 0; }
+                    for (int u = 0; u < U; ++u) {
+                        act[u] = x + 32 * u < hi;
+                        id[u] = act[u] ? __ldg(a.perm_cur + x + 32 * u) : 0;
+                    }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (r * THREADS >= n) break;          // block-uniform: the ballots below stay convergent
-                const int k = r * THREADS + tid;
-                const bool active = k < n;
-                bool drive = false;
-                double u2 = 0.0;
-                if (active && is_zone) {
-                    const int64_t id = ids[r];
-                    double u1;
-                    if (inj) u1 = a.rng.u_drive[id + uoff];
-                    else philox_pair(a.rng, id, (uint32_t)a.step, 0u, u1, u2);
-                    drive = u1 <= pd;                                   // :15 (<=; NaN p_drive parks)
-                    if (drive && inj && !rowzero) u2 = a.rng.u_dest[id + uoff];
-                }
-                const bool search = drive && !rowzero;
-                const bool stay = active && !search;                    // parked, all-zero row (:35-36), or lost (zone 0)
-                const uint32_t m_drive = __ballot_sync(0xffffffffu, drive);
-                const uint32_t m_stay = __ballot_sync(0xffffffffu, stay);
-                const uint32_t m_s = m_drive & ~m_stay;                 // == ballot(search)
-                nd_warp += __popc(m_drive);
-                // stayers: rank among this CTA's cars bound for the own zone, one warp-aggregated shared atomic;
-                // searchers: compact (slot, u_dest) so that phase B runs without idle lanes
-                uint32_t base = 0, off = 0;
-                if (lane == 0) {
-                    if (m_stay) base = atomicAdd(&hist[bin], (uint32_t)__popc(m_stay));
-                    if (m_s) off = atomicAdd(n_search_ctr, (uint32_t)__popc(m_s));
-                }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                off = __shfl_sync(0xffffffffu, off, 0);
-                if (stay) out[k] = (uint32_t)bin | ((base + __popc(m_stay & lt_mask)) << 16);
-                if (search) {
-                    const uint32_t q = off + __popc(m_s & lt_mask);
-                    s.srch_idx[q] = (uint16_t)k;
-                    s.srch_u[q] = u2;
-                }
-            }
-            if (tid == 0) s.misc[pp ^ 1] = 0u;   // the other counter was consumed before the previous barrier
-            __syncthreads();
-
-            // ---- phase B: categorical destination from the staged CDF row (src/resampling.jl:26-49) ----
-            const int n_search = (int)*n_search_ctr;
-            if (need_row) {
-                if (first_chunk) { mbar_wait(&s.bar[0], par & 1u); par ^= 1u; }   // every thread observes the TMA completion
-                const double *row = s.row;
-                const uint16_t *gd = reinterpret_cast<const uint16_t *>(s.row + a.goff);
-                for (int q = tid; q < n_search; q += THREADS) {
-                    const int k = s.srch_idx[q];
-                    const double u2 = s.srch_u[q];
-                    // guided lower_bound on the staged row; acceptance test as in src/resampling.jl:40 (u = 0, u above the
-                    // last entry or a NaN sum -> sentinel 0 = lost)
-                    const int32_t d = cdf_search_guided([&](int32_t j) { return row[j]; }, [&](int32_t bb) { return (int32_t)gd[bb]; },
-                                                        Ni, a.G, u2);
-                    const bool hit = d > 0;
-                    const int dbin = hit ? d - 1 : Ni;
-                    const uint32_t rank = atomicAdd(&hist[dbin], 1u);
-                    out[k] = (uint32_t)dbin | (rank << 16);
-                    if (a.with_time) {                                   // src/resampling.jl:53-70 (time only: counts mode)
-                        if (dbin == bin) t_hi += 300ull;
-                        else if (hit) {
-                            const int64_t id = __ldg(perm + k);
-                            double u3, u4;
-                            if (inj) u3 = a.rng.u_time[id + uoff];
-                            else philox_pair(a.rng, id, (uint32_t)a.step, 1u, u3, u4);
-                            const int64_t od = (int64_t)bin + N * (int64_t)dbin;
-                            double mean, sd;
-                            if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean = ms.x; sd = ms.y; }
-                            else { mean = ldg_stream(a.dm + od + NN * a.hour, l2_stream); sd = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream); }
-                            if (sd == 0.0) sd = 0.1 * mean;
-                            fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));
+                    for (int u = 0; u < U; ++u) {
+                        bool drive = false;
+                        u2[u] = 0.0; cell[u] = 0u;
+                        if (act[u] && is_zone) {
+                            if (INJ) {
+                                drive = a.rng.u_drive[id[u] + uoff] <= pd;                  // :15 (<=; NaN p_drive parks)
+                                if (drive && !rowzero) u2[u] = a.rng.u_dest[id[u] + uoff];
+                            } else {
+                                uint32_t o[4];
+                                philox_words(a.rng, id[u], (uint32_t)a.step, 0u, o);
+                                drive = u52(o[0], o[1]) <= pd;
+                                u2[u] = u52(o[2], o[3]);
+                                cell[u] = o[3] >> a.gshift;   // floor(u2 * G): the top log2(G) bits of the 52-bit uniform
+                            }
+                        }
+                        srch[u] = drive && !rowzero;
+                        stay[u] = act[u] && !srch[u];                                       // parked, all-zero row (:35-36), or lost (bin N)
+                        nd_warp += __popc(__ballot_sync(0xffffffffu, drive));
+                        m_stay[u] = __ballot_sync(0xffffffffu, stay[u]);
+                    }
+                    // stayers: rank among this CTA's cars bound for the own bin, one shared atomic per group
+                    {
+                        unsigned n_stay = 0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) n_stay += __popc(m_stay[u]);
+                        uint32_t base = 0;
+                        if (lane == 0 && n_stay) base = atomicAdd(&hist[z], n_stay);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (stay[u]) a.dr[x + 32 * u] = (uint32_t)z | ((base + __popc(m_stay[u] & lt_mask)) << 16);
+                            base += __popc(m_stay[u]);
                         }
                     }
+                    // ---- phase 2: categorical destination from the staged row (src/resampling.jl:26-49): guided lower_bound,
+                    //      then the acceptance test of :40 (u = 0, u above the last entry or a NaN sum -> bin N = lost) ----
+                    int slo[U], shi[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        slo[u] = shi[u] = Ni;
+                        if (srch[u] && u2[u] > 0.0) {
+                            if (INJ && !(u2[u] < 1.0)) slo[u] = gd[a.G];
+                            else {
+                                const uint32_t c = INJ ? (uint32_t)(u2[u] * (double)a.G) : cell[u];
+                                slo[u] = gd[c]; shi[u] = gd[c + 1];
+                            }
+                        }
+                    }
+                    for (;;) {
+                        bool any = false;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) any |= slo[u] < shi[u];
+                        if (!any) break;
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {   // branch-free: a finished search re-reads row[slo] (slo <= N lies inside the row block)
+                            const bool open = slo[u] < shi[u];
+                            const int mid = (slo[u] + shi[u]) >> 1;
+                            const bool right = row[mid] < u2[u];                                 // NaN compares false -> goes left
+                            slo[u] = (open && right) ? mid + 1 : slo[u];
+                            shi[u] = (open && !right) ? mid : shi[u];
+                        }
+                    }
+                    int dbin[U];
+                    bool far[U];   // a trip to another zone: travel time from the truncated normal
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        dbin[u] = Ni; far[u] = false;
+                        if (srch[u]) {
+                            const bool hit = slo[u] < Ni && u2[u] <= row[slo[u]];
+                            dbin[u] = hit ? slo[u] : Ni;
+                            const uint32_t rank = atomicAdd(&hist[dbin[u]], 1u);
+                            a.dr[x + 32 * u] = (uint32_t)dbin[u] | (rank << 16);
+                            far[u] = hit && dbin[u] != z;
+                            if (TIME && dbin[u] == z) t_hi += 300ull;                           // :58-59
+                        }
+                    }
+                    // ---- phase 3 (time only: counts mode), src/resampling.jl:53-70 ----
+                    if (TIME) {
+                        double mean[U], sd[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            mean[u] = sd[u] = 0.0;
+                            if (far[u]) {
+                                const int64_t od = (int64_t)z + N * (int64_t)dbin[u];
+                                if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean[u] = ms.x; sd[u] = ms.y; }
+                                else {
+                                    mean[u] = ldg_stream(a.dm + od + NN * a.hour, l2_stream);
+                                    sd[u] = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (far[u]) {
+                                double u3;
+                                if (INJ) u3 = a.rng.u_time[id[u] + uoff];
+                                else { uint32_t o[4]; philox_words(a.rng, id[u], (uint32_t)a.step, 1u, o); u3 = u52(o[0], o[1]); }
+                                double s = sd[u];
+                                if (s == 0.0) s = 0.1 * mean[u];
+                                fx_add(t_hi, t_lo, truncnormal(mean[u], s, u3));
+                            }
+                    }
+                }
+                rot += ngroups;
+                if (is_zone && lane == 0 && nd_warp) {
+                    atomicAdd(a.drv + z, nd_warp);                                             // src/saveresults.jl:13-15
+                    if (TIME && rowzero) t_hi += 300ull * nd_warp;                             // origin == destination: 5 min (:58-59)
                 }
             }
-            __syncthreads();
-            pp ^= 1;
+            // this warp is through with bin z; the last warp to say so re-arms the buffer with the bin R further on
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done[slot], 1u) == (uint32_t)(W - 1)) {
+                    done[slot] = 0u;
+                    const int zn = z + R;
+                    if (zn < NB && __ldg(a.start + zn) < slab_hi) issue(zn, slot);
+                }
+            }
         }
-        if (is_zone) {
-            if (rowzero && a.with_time && lane == 0) t_hi += 300ull * nd_warp;   // origin == destination: 5 min (:58-59)
-            if (lane == 0 && nd_warp) atomicAdd(a.drv + bin, nd_warp);             // src/saveresults.jl:13-15
-        } else if (tid == 0) lost += (unsigned long long)(seg_end - pos);
-        pos = seg_end;
-        ++z;
-    }
-
-    // this CTA's histogram row: M[g][bin] = cars of slab g bound for bin
-    uint32_t *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
-    for (int x = tid; x < NB; x += THREADS) Mrow[x] = hist[x];
-
-    // driving-time and lost-car totals: integer block reduction, a few global atomics per CTA
-    __shared__ unsigned long long red[3];
-    if (tid < 3) red[tid] = 0ull;
-    __syncthreads();
-    t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo); lost = warp_sum_u64(lost);
-    if (lane == 0) {
-        if (t_hi) atomicAdd(&red[0], t_hi);
-        if (t_lo) atomicAdd(&red[1], t_lo);
-        if (lost) atomicAdd(&red[2], lost);
     }
     __syncthreads();
-    if (tid == 0) {
-        const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
-        if (hi) atomicAdd(a.t_hi, hi);
-        if (lo32) atomicAdd(a.t_lo, lo32);
-        if (red[2]) atomicAdd(a.lost, red[2]);
+
+    // One global atomic per destination this CTA saw: the return value is where this CTA's cars start inside the
+    // destination's bucket.  The counters are one per 256 bytes (one L2 slice each: profiles/r2 micro-benchmark C).
+    {
+        uint2 *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
+        constexpr int B = 4;
+        for (int b0 = tid; b0 < NB; b0 += B * THREADS) {
+            uint32_t h[B], gb[B];
+#pragma unroll
+            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; h[q] = b < NB ? hist[b] : 0u; }
+#pragma unroll
+            for (int q = 0; q < B; ++q) gb[q] = h[q] ? atomicAdd(a.tot + (size_t)(b0 + q * THREADS) * kTotStride, h[q]) : 0u;
+#pragma unroll
+            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; if (b < NB) Mrow[b] = make_uint2(h[q], gb[q]); }
+        }
+    }
+
+    // driving-time total: integer block reduction, two global atomics per CTA
+    if (TIME) {
+        t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo);
+        if (lane == 0) {
+            if (t_hi) atomicAdd(&red[0], t_hi);
+            if (t_lo) atomicAdd(&red[1], t_lo);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
+            if (hi) atomicAdd(a.t_hi, hi);
+            if (lo32) atomicAdd(a.t_lo, lo32);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_bucket_colscan: M[g][b] <- sum_{g' < g} M[g'][b] (exclusive, in place); cnt_next[b] <- sum_g M[g][b].
-// One CTA per 32 destination columns: 32 x 32 threads, each sums / rescans a stripe of slabs; coalesced 128 B rows.
-// ------------------------------------------------------------------------------------------------
-template <int PER, int COLS, int PARTS>   // PER >= ceil(G / PARTS): the stripe of one thread lives in registers (one pass over M)
-__global__ void __launch_bounds__(COLS * PARTS) k_bucket_colscan(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
-{
-    __shared__ uint32_t ps[PARTS][COLS + 1];
-    pdl_trigger();
-    pdl_wait();
-    const int col = threadIdx.x % COLS, part = threadIdx.x / COLS;
-    const int c = blockIdx.x * COLS + col;
-    const int per = (G + PARTS - 1) / PARTS;
-    const int g0 = min(G, part * per), g1 = min(G, g0 + per);
-    const bool live = c < NB;
-    uint32_t v[PER];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int u = 0; u < PER; ++u) {
-        const int g = g0 + u;
-        v[u] = (live && g < g1) ? M[(size_t)g * NB + c] : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < PER; ++u) sum += v[u];
-    ps[part][col] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int p = 0; p < part; ++p) run += ps[p][col];
-    if (live) {
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const int g = g0 + u;
-            if (g < g1) M[(size_t)g * NB + c] = run;
-            run += v[u];
-        }
-        if (part == PARTS - 1) cnt_next[c] = run;   // the last stripe ends with the column total
-    }
-}
-
-// general fallback (any G): two passes over the stripe
-__global__ void __launch_bounds__(1024) k_bucket_colscan_any(uint32_t *__restrict__ M, int G, int NB, uint32_t *__restrict__ cnt_next)
-{
-    __shared__ uint32_t ps[32][33];
-    pdl_trigger();
-    pdl_wait();
-    const int c = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5;
-    const int per = (G + 31) / 32;
-    const int g0 = min(G, part * per), g1 = min(G, g0 + per);
-    const bool live = c < NB;
-    uint32_t sum = 0;
-    if (live) for (int g = g0; g < g1; ++g) sum += M[(size_t)g * NB + c];
-    ps[part][threadIdx.x & 31] = sum;
-    __syncthreads();
-    uint32_t run = 0;
-    for (int p = 0; p < part; ++p) run += ps[p][threadIdx.x & 31];
-    if (live) {
-        for (int g = g0; g < g1; ++g) {
-            const size_t k = (size_t)g * NB + c;
-            const uint32_t v = M[k];
-            M[k] = run;
-            run += v;
-        }
-        if (part == 31) cnt_next[c] = run;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// exclusive block scan of v[0..n) in place (v in shared memory); returns the total.  blockDim.x <= 1024.
+// exclusive block scans in place (arrays in shared memory); blockDim.x <= 1024
 // ------------------------------------------------------------------------------------------------
 __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot /*[33]*/)
 {
@@ -361,69 +340,132 @@ __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot 
     return warp_tot[32];
 }
 
+// two arrays at once (one pass of shuffles and barriers); returns the total of v2
+__device__ uint32_t block_exclusive_scan2(uint32_t *v1, uint32_t *v2, int n, uint32_t *wt /*[66]*/)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (n + nt - 1) / nt;
+    const int b = tid * per, e = min(b + per, n);
+    uint32_t s1 = 0, s2 = 0;
+    for (int k = b; k < e; ++k) { s1 += v1[k]; s2 += v2[k]; }
+    uint32_t i1 = s1, i2 = s2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
+        if (lane >= o) { i1 += y1; i2 += y2; }
+    }
+    if (lane == 31) { wt[wid] = i1; wt[33 + wid] = i2; }
+    __syncthreads();
+    if (wid == 0) {
+        const bool in = lane < (nt + 31) / 32;
+        const uint32_t t1 = in ? wt[lane] : 0u, t2 = in ? wt[33 + lane] : 0u;
+        uint32_t a1 = t1, a2 = t2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y1 = __shfl_up_sync(0xffffffffu, a1, o), y2 = __shfl_up_sync(0xffffffffu, a2, o);
+            if (lane >= o) { a1 += y1; a2 += y2; }
+        }
+        wt[lane] = a1 - t1; wt[33 + lane] = a2 - t2;
+        if (lane == 31) { wt[32] = a1; wt[65] = a2; }
+    }
+    __syncthreads();
+    uint32_t r1 = wt[wid] + i1 - s1, r2 = wt[33 + wid] + i2 - s2;
+    for (int k = b; k < e; ++k) {
+        const uint32_t c1 = v1[k], c2 = v2[k];
+        v1[k] = r1; v2[k] = r2;
+        r1 += c1; r2 += c2;
+    }
+    __syncthreads();
+    return wt[65];
+}
+
+// largest z in [0, nb) with start[z] <= x (start non-decreasing, start[0] = 0): the bin that holds slot x
+__device__ __forceinline__ int bin_of_slot(const uint32_t *start, int nb, uint32_t x)
+{
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (start[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_bucket_scatter: cars move to their destination bucket (state update, src/resampling.jl:81-83).
-// CTA g handles the slab CTA g of k_bucket_sample handled: off[b] = start_next[b] + M[g][b].
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_bucket_scatter(const ScatterArgs a)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(const ScatterArgs a)
 {
-    extern __shared__ uint32_t sm[];   // off[NB] | mrow[NB] | warp_tot[33]
-    const int NB = a.NB;
-    uint32_t *off = sm, *mrow = sm + NB, *warp_tot = sm + 2 * NB;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int NB = a.NB, NBp = (NB + 3) & ~3;
+    const int tid = threadIdx.x;
+    uint32_t *const lstart = reinterpret_cast<uint32_t *>(sm_raw);   // [NBp] first position of every destination inside the sorted slab
+    uint32_t *const off = lstart + NBp;                               // [NBp] bucket starts, then global position minus sorted position
+    uint32_t *const wt = off + NBp;                                   // [72]
+    int32_t *const sid = reinterpret_cast<int32_t *>(wt + 72);        // [slab] car ids sorted by destination
+    uint16_t *const sdst = reinterpret_cast<uint16_t *>(sid + ((a.slab + 3) & ~(int64_t)3));   // [slab] their destinations
     pdl_trigger();
     pdl_wait();
-    const uint32_t *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
     const int lo = (int)min((int64_t)blockIdx.x * a.slab, a.C), hi = (int)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
+    const uint2 *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
     const uint32_t *__restrict__ dr = a.dr;
     const int32_t *__restrict__ pc = a.perm_cur;
-    // every global load this CTA needs is issued up front (slot data of the first batch, bucket sizes, its M row),
-    // so the prefix sum below runs under their latency
-    constexpr int PS = 16, PRE = 4;
+    // every global load of the first batch of slots is issued up front: the scans below run under their latency
+    constexpr int PS = 16;
     uint32_t v[PS];
     int32_t id[PS];
 #pragma unroll
     for (int u = 0; u < PS; ++u) {
-        const int sl = lo + u * 256 + threadIdx.x;
+        const int sl = lo + u * THREADS + tid;
         v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
         id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
     }
-    for (int x0 = 0; x0 < NB; x0 += PRE * 256) {
-        uint32_t c[PRE], m[PRE];
-#pragma unroll
-        for (int u = 0; u < PRE; ++u) {
-            const int x = x0 + u * 256 + threadIdx.x;
-            c[u] = (x < NB) ? __ldg(a.cnt_next + x) : 0u;
-            m[u] = (x < NB) ? __ldg(Mrow + x) : 0u;
+    for (int x = tid; x < NB; x += THREADS) {
+        lstart[x] = __ldg(&Mrow[x].x);
+        off[x] = __ldg(a.tot + (size_t)x * kTotStride);
+    }
+    __syncthreads();
+    const uint32_t total = block_exclusive_scan2(lstart, off, NB, wt);
+    if (blockIdx.x == 0) {   // bucket starts and sizes of the next step (the sizes are its parked-car histogram)
+        for (int x = tid; x < NB; x += THREADS) {
+            a.start_next[x] = off[x];
+            a.cnt_next[x] = (x + 1 < NB ? off[x + 1] : total) - off[x];
+            a.tot_zero[(size_t)x * kTotStride] = 0u;   // the counters of the step after this one
         }
-#pragma unroll
-        for (int u = 0; u < PRE; ++u) { const int x = x0 + u * 256 + threadIdx.x; if (x < NB) { off[x] = c[u]; mrow[x] = m[u]; } }
+        if (tid == 0) a.start_next[NB] = total;
     }
+    if (tid == 0) a.first_zone_next[blockIdx.x] = (uint32_t)bin_of_slot(off, NB, (uint32_t)lo);
     __syncthreads();
-    const uint32_t total = block_exclusive_scan(off, NB, warp_tot);
-    if (blockIdx.x == 0) {   // bucket starts of the next step, for the next k_bucket_sample
-        for (int x = threadIdx.x; x < NB; x += blockDim.x) a.start_next[x] = off[x];
-        if (threadIdx.x == 0) a.start_next[NB] = total;
-    }
-    for (int x = threadIdx.x; x < NB; x += blockDim.x) off[x] += mrow[x];
+    for (int x = tid; x < NB; x += THREADS) off[x] += __ldg(&Mrow[x].y) - lstart[x];
     __syncthreads();
-    for (int s0 = lo; s0 < hi; s0 += PS * 256) {
+    // pass 1: sort the slab by destination in shared memory
+    for (int s0 = lo; s0 < hi; s0 += PS * THREADS) {
         if (s0 > lo) {   // slabs larger than one register batch
 #pragma unroll
             for (int u = 0; u < PS; ++u) {
-                const int sl = s0 + u * 256 + threadIdx.x;
+                const int sl = s0 + u * THREADS + tid;
                 v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
                 id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
             }
         }
 #pragma unroll
         for (int u = 0; u < PS; ++u) {
-            const int sl = s0 + u * 256 + threadIdx.x;
+            const int sl = s0 + u * THREADS + tid;
             if (sl < hi) {
-                const int db = (int)(v[u] & 0xffffu);
-                a.perm_next[off[db] + (v[u] >> 16)] = id[u];
-                if (a.zone_out) a.zone_out[id[u]] = (db < NB - 1) ? db + 1 : 0;   // last step: car-id indexed state
+                const uint32_t d = v[u] & 0xffffu, p = lstart[d] + (v[u] >> 16);
+                sid[p] = id[u];
+                sdst[p] = (uint16_t)d;
             }
         }
+    }
+    __syncthreads();
+    // pass 2: consecutive threads hold consecutive cars of one destination -> the stores go out in runs
+    const int n = hi - lo;
+    for (int p = tid; p < n; p += THREADS) {
+        const uint32_t d = sdst[p];
+        const int32_t car = sid[p];
+        a.perm_next[off[d] + (uint32_t)p] = car;
+        if (a.zone_out) a.zone_out[car] = (d < (uint32_t)(NB - 1)) ? (int32_t)d + 1 : 0;   // last step: car-id indexed state
     }
 }
 
@@ -443,8 +485,9 @@ __global__ void __launch_bounds__(256) k_bucket_hist(const int32_t *__restrict__
     }
 }
 
-// start[0..NB] = exclusive scan of cnt[0..NB) (+ total)
-__global__ void __launch_bounds__(1024) k_bucket_start(const uint32_t *__restrict__ cnt, int NB, uint32_t *__restrict__ start)
+// start[0..NB] = exclusive scan of cnt[0..NB) (+ total); first_zone[g] = the bin that holds the first slot of slab g
+__global__ void __launch_bounds__(1024) k_bucket_start(const uint32_t *__restrict__ cnt, int NB, uint32_t *__restrict__ start,
+                                                       uint32_t *__restrict__ first_zone, int n_slabs, int64_t slab, int64_t C)
 {
     extern __shared__ uint32_t sm[];   // v[NB] | warp_tot[33]
     uint32_t *v = sm, *warp_tot = sm + NB;
@@ -453,6 +496,8 @@ __global__ void __launch_bounds__(1024) k_bucket_start(const uint32_t *__restric
     const uint32_t total = block_exclusive_scan(v, NB, warp_tot);
     for (int x = threadIdx.x; x < NB; x += blockDim.x) start[x] = v[x];
     if (threadIdx.x == 0) start[NB] = total;
+    for (int g = threadIdx.x; g < n_slabs; g += blockDim.x)
+        first_zone[g] = (uint32_t)bin_of_slot(v, NB, (uint32_t)min((int64_t)g * slab, C));
 }
 
 __global__ void __launch_bounds__(256) k_bucket_place(const int32_t *__restrict__ zone, int64_t C, int NB,
@@ -473,15 +518,22 @@ __global__ void __launch_bounds__(256) k_bucket_place(const int32_t *__restrict_
     }
 }
 
-// counts in the public layout: parking/driving uint32 [N, n_steps] from the bucket arrays with stride NB = N + 1
+// counts in the public layout: parking/driving uint32 [N, n_steps] from the bucket arrays with stride NB = N + 1; the
+// lost-car visits of the day are the sizes of bin N over the steps (documented extension, DESIGN.md "sentinel")
 __global__ void k_bucket_export_counts(const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ drv, int N, int64_t n_steps,
-                                       uint32_t *__restrict__ parking, uint32_t *__restrict__ driving)
+                                       uint32_t *__restrict__ parking, uint32_t *__restrict__ driving, unsigned long long *lost)
 {
     const int64_t n = (int64_t)N * n_steps;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t s = k / N, z = k % N;
         parking[k] = cnt[s * (N + 1) + z];
         driving[k] = drv[s * (N + 1) + z];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        unsigned long long v = 0ull;
+        for (int64_t s = threadIdx.x; s < n_steps; s += 32) v += cnt[s * (N + 1) + N];
+        v = warp_sum_u64(v);
+        if (threadIdx.x == 0) *lost = v;
     }
 }
 
@@ -497,51 +549,69 @@ __global__ void k_finalize_time(unsigned long long *hi, unsigned long long *lo, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// launchers
+// geometry and launchers
 // ------------------------------------------------------------------------------------------------
-// Two shapes: small CTAs (256 threads, chunks of 1,024 cars) so that four fit on an SM when the CDF row is
-// small (N up to ~3,000), otherwise 512 threads / 2,048 cars with as many CTAs as shared memory allows.
-static int bucket_shape(int64_t N, int64_t ldc, size_t *smem_out, int *ctas_out)
+static int env_int(const char *name, int dflt)
 {
-    const size_t small = sample_smem_bytes(N, ldc, 1024), big = sample_smem_bytes(N, ldc, 2048);
-    const size_t sm_total = 227 * 1024;
-    if (4 * (small + 1024) <= sm_total) { *smem_out = small; *ctas_out = 4; return 1; }   // 4 x 256 x 64 regs fill the register file
-    if (big + 1024 <= sm_total) { *smem_out = big; *ctas_out = (2 * (big + 1024) <= sm_total) ? 2 : 1; return 2; }
-    return 0;
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+static size_t scatter_smem(int NB, int64_t slab)
+{
+    const size_t NBp = (size_t)((NB + 3) & ~3);
+    return 2 * NBp * 4 + 72 * 4 + (size_t)((slab + 3) & ~(int64_t)3) * 4 + (size_t)((slab + 7) & ~(int64_t)7) * 2;
+}
+
+// Slabs (= CTAs of both kernels), slab size, CTA width and ring depth.  One fat CTA per SM: a slab as large as the
+// 16-bit rank and the scatter kernel's shared-memory sort allow, more slabs (whole waves) only beyond that.
+bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g)
+{
+    if (N + 1 > 65535 || C < 1 || C > 0x7fffffff) return false;
+    const int NB = (int)N + 1;
+    const int threads = env_int("CPM_BUCKET_THREADS", 1024) == 512 ? 512 : 1024;
+    const int per_sm = 1024 / threads;
+    const size_t cap = kSmemCap / per_sm - (per_sm > 1 ? 1024 : 0);
+    const size_t fixed1 = hist_bytes(N) + kSampleTail, row = (size_t)ldc * 8;
+    if (fixed1 + row > cap) return false;
+    int ring = (int)std::min<size_t>(kMaxRing, (cap - fixed1) / row);
+    const int ring_env = env_int("CPM_BUCKET_RING", 0);
+    if (ring_env >= 1 && ring_env < ring) ring = ring_env;
+    const size_t fixed2 = scatter_smem(NB, 0) + 64;
+    if (fixed2 + 6 * 256 > cap) return false;
+    int64_t slab_cap = (int64_t)((cap - fixed2) / 6) & ~(int64_t)63;
+    if (slab_cap > 65472) slab_cap = 65472;
+    const int64_t wave = (int64_t)kSMs * per_sm;
+    int64_t n = (C + 255) / 256;
+    if (n > wave) n = wave;
+    if (n * slab_cap < C) n = ((C + slab_cap - 1) / slab_cap + wave - 1) / wave * wave;
+    g->n_slabs = (int)n;
+    g->slab = (C + n - 1) / n;
+    g->threads = threads;
+    g->ring = ring;
+    g->smem_sample = fixed1 + (size_t)ring * row;
+    g->smem_scatter = scatter_smem(NB, g->slab);
+    return true;
 }
 
 bool bucket_supported(int64_t N, int64_t ldc)
 {
-    size_t smem; int ctas;
-    return N + 1 <= 65535 && bucket_shape(N, ldc, &smem, &ctas) != 0;
+    BucketGeom g;
+    return bucket_geometry(N, ldc, 1, &g);
 }
 
-// number of slabs (= CTAs of k_bucket_sample / k_bucket_scatter) and slab size: one resident wave, more only when a
-// slab would exceed the 16-bit rank range
-void bucket_grid(int64_t N, int64_t ldc, int64_t C, int *G_out, int64_t *slab_out)
-{
-    size_t smem = 0; int ctas = 1;
-    bucket_shape(N, ldc, &smem, &ctas);
-    int64_t G = (int64_t)kSMs * ctas;
-    const int64_t min_G = (C + 65534) / 65535;
-    if (G < min_G) G = min_G;
-    if (G > C) G = C > 0 ? C : 1;
-    *G_out = (int)G;
-    *slab_out = (C + G - 1) / G;
-}
-
-// opt in to > 48 KB of dynamic shared memory, raising the per-kernel limit only when a launch needs more
+// opt in to > 48 KB of dynamic shared memory.  The attribute belongs to the CURRENT device's copy of the kernel, so it
+// is set on every launch (a cheap host-side call) instead of being cached in a process-wide flag: contexts on
+// several devices and host threads share this library.
 template <typename K>
-static void ensure_smem(K kernel, size_t bytes, size_t &granted)
+static cudaError_t ensure_smem(K kernel, size_t bytes)
 {
-    if (bytes > granted) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        granted = bytes;
-    }
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
 template <typename... KArgs, typename... Args>
-static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args)
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -549,63 +619,60 @@ static void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, args...);
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st)
+template <int THREADS, int U>
+static cudaError_t launch_sample_variant(const BucketArgs &a, const BucketGeom &g, cudaStream_t st)
 {
-    size_t smem = 0; int ctas = 0;
-    const int shape = bucket_shape(a.N, a.ldc, &smem, &ctas);
-    static size_t granted[4] = {0, 0, 0, 0};
-    const bool inj = a.rng.mode == 1;
-    if (shape == 1) {
-        if (inj) { ensure_smem(k_bucket_sample<256, 1024, true>, smem, granted[0]); launch_pdl(k_bucket_sample<256, 1024, true>, G, 256, smem, st, a); }
-        else     { ensure_smem(k_bucket_sample<256, 1024, false>, smem, granted[1]); launch_pdl(k_bucket_sample<256, 1024, false>, G, 256, smem, st, a); }
-    } else if (shape == 2) {
-        if (inj) { ensure_smem(k_bucket_sample<512, 2048, true>, smem, granted[2]); launch_pdl(k_bucket_sample<512, 2048, true>, G, 512, smem, st, a); }
-        else     { ensure_smem(k_bucket_sample<512, 2048, false>, smem, granted[3]); launch_pdl(k_bucket_sample<512, 2048, false>, G, 512, smem, st, a); }
-    } else return -1;
-    return 1;
+    const bool inj = a.rng.mode == 1, time = a.with_time != 0;
+    void (*k)(const BucketArgs) = inj ? (time ? k_bucket_sample<THREADS, U, true, true> : k_bucket_sample<THREADS, U, true, false>)
+                                      : (time ? k_bucket_sample<THREADS, U, false, true> : k_bucket_sample<THREADS, U, false, false>);
+    cudaError_t e = ensure_smem(k, g.smem_sample);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(k, (unsigned)g.n_slabs, THREADS, g.smem_sample, st, a);
 }
 
-int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaStream_t st)
+int launch_bucket_sample(const BucketArgs &a, const BucketGeom &g, cudaStream_t st)
 {
-    // 8 columns x 64 stripes per CTA: ~NB/8 CTAs (two per SM at Melbourne scale) instead of NB/32 on half of the SMs
-    const int per64 = (G + 63) / 64, per32 = (G + 31) / 32;
-    if (per64 <= 10) launch_pdl(k_bucket_colscan<10, 8, 64>, (NB + 7) / 8, 512, 0, st, M, G, NB, cnt_next);
-    else if (per32 <= 40) launch_pdl(k_bucket_colscan<40, 32, 32>, (NB + 31) / 32, 1024, 0, st, M, G, NB, cnt_next);
-    else launch_pdl(k_bucket_colscan_any, (NB + 31) / 32, 1024, 0, st, M, G, NB, cnt_next);
-    return 1;
+    static const int U = env_int("CPM_BUCKET_U", 2) == 1 ? 1 : 2;
+    cudaError_t e;
+    if (g.threads == 512) e = (U == 1) ? launch_sample_variant<512, 1>(a, g, st) : launch_sample_variant<512, 2>(a, g, st);
+    else e = (U == 1) ? launch_sample_variant<1024, 1>(a, g, st) : launch_sample_variant<1024, 2>(a, g, st);
+    return e == cudaSuccess ? 1 : -1;
 }
 
-static size_t scan_smem(int NB) { return ((size_t)2 * NB + 40) * sizeof(uint32_t); }
-
-int launch_bucket_scatter(const ScatterArgs &a, int G, cudaStream_t st)
+int launch_bucket_scatter(const ScatterArgs &a, const BucketGeom &g, cudaStream_t st)
 {
-    static size_t granted = 48 * 1024;
-    ensure_smem(k_bucket_scatter, scan_smem(a.NB), granted);
-    launch_pdl(k_bucket_scatter, G, 256, scan_smem(a.NB), st, a);
-    return 1;
+    cudaError_t e;
+    if (g.threads == 512) {
+        e = ensure_smem(k_bucket_scatter<512>, g.smem_scatter);
+        if (e == cudaSuccess) e = launch_pdl(k_bucket_scatter<512>, (unsigned)g.n_slabs, 512, g.smem_scatter, st, a);
+    } else {
+        e = ensure_smem(k_bucket_scatter<1024>, g.smem_scatter);
+        if (e == cudaSuccess) e = launch_pdl(k_bucket_scatter<1024>, (unsigned)g.n_slabs, 1024, g.smem_scatter, st, a);
+    }
+    return e == cudaSuccess ? 1 : -1;
 }
 
 int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start, uint32_t *cursor_tmp,
-                     int32_t *perm, cudaStream_t st)
+                     int32_t *perm, uint32_t *first_zone, const BucketGeom &g, cudaStream_t st)
 {
-    cudaMemsetAsync(cnt0, 0, (size_t)NB * sizeof(uint32_t), st);
-    cudaMemsetAsync(cursor_tmp, 0, (size_t)NB * sizeof(uint32_t), st);
-    const int g = sampler_grid(C);
-    k_bucket_hist<<<g, 256, 0, st>>>(zone, C, NB, cnt0);
-    static size_t granted = 48 * 1024;
-    ensure_smem(k_bucket_start, scan_smem(NB), granted);
-    k_bucket_start<<<1, 1024, scan_smem(NB), st>>>(cnt0, NB, start);
-    k_bucket_place<<<g, 256, 0, st>>>(zone, C, NB, start, cursor_tmp, perm);
+    if (cudaMemsetAsync(cnt0, 0, (size_t)NB * sizeof(uint32_t), st) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(cursor_tmp, 0, (size_t)NB * sizeof(uint32_t), st) != cudaSuccess) return -1;
+    const int grid = sampler_grid(C);
+    k_bucket_hist<<<grid, 256, 0, st>>>(zone, C, NB, cnt0);
+    const size_t smem = ((size_t)NB + 40) * sizeof(uint32_t);
+    if (ensure_smem(k_bucket_start, smem) != cudaSuccess) return -1;
+    k_bucket_start<<<1, 1024, smem, st>>>(cnt0, NB, start, first_zone, g.n_slabs, g.slab, C);
+    k_bucket_place<<<grid, 256, 0, st>>>(zone, C, NB, start, cursor_tmp, perm);
     return 3;
 }
 
 int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
-                                uint32_t *driving, cudaStream_t st)
+                                uint32_t *driving, unsigned long long *lost, cudaStream_t st)
 {
-    k_bucket_export_counts<<<sampler_grid((int64_t)N * n_steps), 256, 0, st>>>(cnt, drv, N, n_steps, parking, driving);
+    k_bucket_export_counts<<<sampler_grid((int64_t)N * n_steps), 256, 0, st>>>(cnt, drv, N, n_steps, parking, driving, lost);
     return 1;
 }
 

@@ -54,12 +54,12 @@ static int32_t fail(int32_t code, const char *fmt, const char *a = "", const cha
 // on a block is stream-ordered on the context's streams and every destroy synchronises first, so handing a block to its
 // next owner needs no further synchronisation.  The cache is emptied when an allocation fails and at cpm_ctx_destroy.
 struct BlockCache {
-    std::multimap<size_t, void *> free_blocks[16];
+    std::map<int, std::multimap<size_t, void *>> free_blocks;   // per device ordinal
     std::mutex mu;   // contexts of different host threads may share a device
     void *take(int dev, size_t bytes, size_t *cap)
     {
         std::lock_guard<std::mutex> lock(mu);
-        auto &m = free_blocks[dev & 15];
+        auto &m = free_blocks[dev];
         auto it = m.lower_bound(bytes);
         if (it == m.end() || it->first > 2 * bytes + (1u << 20)) return nullptr;
         void *p = it->second;
@@ -70,12 +70,12 @@ struct BlockCache {
     void give(int dev, void *p, size_t cap)
     {
         std::lock_guard<std::mutex> lock(mu);
-        free_blocks[dev & 15].emplace(cap, p);
+        free_blocks[dev].emplace(cap, p);
     }
     void flush(int dev)
     {
         std::lock_guard<std::mutex> lock(mu);
-        auto &m = free_blocks[dev & 15];
+        auto &m = free_blocks[dev];
         for (auto &kv : m) cudaFree(kv.second);
         m.clear();
     }
@@ -159,8 +159,11 @@ struct cpm_fleet {
     // grouped by zone bin (bucket sampler); each is rebuilt lazily from the other
     bool zone_valid = true, bucket_valid = false;
     int64_t bucket_N = 0;
+    BucketGeom geom = {};     // slab partition of the current grouping (first_zone depends on it)
     int cur = 0;
-    DevBuf perm[2], dest, pos, bcnt, bdrv, cnt_cur, start_tmp, cursor_tmp, items, n_items, lost_acc;
+    // perm: car ids grouped by bin; dest: (destination, rank) per slot; pos: per-slab {count, first position} rows;
+    // tot: two padded per-destination arrival counter arrays (ping-pong over the steps); first_zone: per slab
+    DevBuf perm[2], dest, pos, tot, first_zone, bcnt, bdrv, cnt_cur, start_tmp, cursor_tmp, lost_acc;
 };
 
 struct Scalars {   // device-side scalar block of a fleet
@@ -290,6 +293,10 @@ extern "C" int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int
 
 static int32_t check_launch(cpm_ctx *ctx, int n)
 {
+    if (n < 0) {   // a launcher's own CUDA call (attribute, memset, launch) failed: report that call's error
+        const cudaError_t e = cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? CPM_ERR_OOM : CPM_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    }
     ctx->launches += n;
     CU(cudaGetLastError());
     return CPM_OK;
@@ -314,6 +321,7 @@ extern "C" int32_t cpm_city_destroy(cpm_city *c)
     if (!c) return CPM_OK;
     cudaSetDevice(c->ctx->device);
     if (c->ctx->aux_st) cudaStreamSynchronize(c->ctx->aux_st);   // a failed pass may have left the createpdrive chain unjoined
+    if (c->ctx->copy_st) cudaStreamSynchronize(c->ctx->copy_st); // an upload may still be writing into this city's blocks
     cudaStreamSynchronize(c->ctx->st);
     c->dm.release(); c->dist.release(); c->rdist.release(); c->msd.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
     c->norm.release(); c->cdf.release(); c->rowzero.release();
@@ -569,9 +577,11 @@ extern "C" int32_t cpm_fleet_destroy(cpm_fleet *f)
 {
     if (!f) return CPM_OK;
     cudaSetDevice(f->ctx->device);
+    if (f->ctx->aux_st) cudaStreamSynchronize(f->ctx->aux_st);
+    if (f->ctx->copy_st) cudaStreamSynchronize(f->ctx->copy_st);
     cudaStreamSynchronize(f->ctx->st);
     DevBuf *bufs[] = { &f->zone, &f->counts, &f->scalars, &f->norm_out, &f->perm[0], &f->perm[1], &f->dest, &f->pos, &f->bcnt,
-                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->items, &f->n_items, &f->lost_acc };
+                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->tot, &f->first_zone, &f->lost_acc };
     for (DevBuf *b : bufs) b->release();
     delete f;
     return CPM_OK;
@@ -620,10 +630,12 @@ extern "C" int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src)
         const size_t NB = (size_t)src->bucket_N + 1;
         TRY(dst->perm[0].ensure((size_t)dst->C * 4));
         TRY(dst->cnt_cur.ensure(NB * 4)); TRY(dst->start_tmp.ensure((NB + 1) * 4));
+        TRY(dst->first_zone.ensure((size_t)src->geom.n_slabs * 4));
         CU(cudaMemcpyAsync(dst->perm[0].p, src->perm[src->cur].p, (size_t)dst->C * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
         CU(cudaMemcpyAsync(dst->cnt_cur.p, src->cnt_cur.p, NB * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
         CU(cudaMemcpyAsync(dst->start_tmp.p, src->start_tmp.p, (NB + 1) * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
-        dst->cur = 0; dst->bucket_valid = true; dst->bucket_N = src->bucket_N;
+        CU(cudaMemcpyAsync(dst->first_zone.p, src->first_zone.p, (size_t)src->geom.n_slabs * 4, cudaMemcpyDeviceToDevice, dst->ctx->st));
+        dst->cur = 0; dst->bucket_valid = true; dst->bucket_N = src->bucket_N; dst->geom = src->geom;
     }
     return CPM_OK;
 }
@@ -707,22 +719,27 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
 }
 
 // bucket sampler: cars grouped by zone, CDF rows staged in shared memory (bucket.cu)
-// Group the cars of a fleet by zone from its car-id indexed zone array: perm[0] (car ids by bin), the bucket starts and
-// the bucket sizes (cnt_cur).  Leaves the fleet in the state a finished bucket day leaves it in.
-static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N, cudaStream_t st = nullptr)
+// Group the cars of a fleet by zone from its car-id indexed zone array: perm[0] (car ids by bin), the bucket starts, the
+// bucket sizes (cnt_cur) and the first bin of every slab.  Leaves the fleet in the state a finished bucket day leaves it in.
+static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N, int64_t ldc, cudaStream_t st = nullptr)
 {
     cpm_ctx *ctx = f->ctx;
     if (!st) st = ctx->st;
     const int NB = (int)N + 1;
     if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
+    BucketGeom g;
+    if (!bucket_geometry(N, ldc, f->C, &g)) return fail(CPM_ERR_ARG, "the bucket sampler does not support this city size");
     TRY(f->perm[0].ensure((size_t)f->C * 4));
     TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
+    TRY(f->first_zone.ensure((size_t)g.n_slabs * 4));
     f->cur = 0;
     LAUNCH(ctx, launch_bucketize(f->zone.as<int32_t>(), f->C, NB, f->cnt_cur.as<uint32_t>(), f->start_tmp.as<uint32_t>(),
-                                 f->cursor_tmp.as<uint32_t>(), f->perm[0].as<int32_t>(), st));
-    f->bucket_valid = true; f->bucket_N = N;
+                                 f->cursor_tmp.as<uint32_t>(), f->perm[0].as<int32_t>(), f->first_zone.as<uint32_t>(), g, st));
+    f->bucket_valid = true; f->bucket_N = N; f->geom = g;
     return CPM_OK;
 }
+
+static int ilog2(int64_t v) { int l = 0; while ((1ll << (l + 1)) <= v) ++l; return l; }
 
 static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
 {
@@ -730,36 +747,45 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     const int64_t N = city->N, C = f->C;
     const int NB = (int)N + 1;
     const int64_t S = o->n_steps;
-    int G = 0; int64_t slab = 0;
-    bucket_grid(N, city->ldc, C, &G, &slab);
+    BucketGeom g;
+    if (!bucket_geometry(N, city->ldc, C, &g)) return fail(CPM_ERR_ARG, "the bucket sampler does not support this city size");
+    const size_t tot_words = (size_t)NB * kTotStride;
     TRY(f->perm[0].ensure((size_t)C * 4)); TRY(f->perm[1].ensure((size_t)C * 4));
     TRY(f->dest.ensure((size_t)C * 4));                                   // (destination, rank) per slot
-    TRY(f->pos.ensure((size_t)G * NB * 4));                               // per-slab destination histograms
+    TRY(f->pos.ensure((size_t)g.n_slabs * NB * sizeof(uint2)));           // per-slab {count, first position} rows
+    TRY(f->tot.ensure(2 * tot_words * 4));
+    TRY(f->first_zone.ensure((size_t)g.n_slabs * 4));
     TRY(f->bcnt.ensure((size_t)(S + 1) * NB * 4)); TRY(f->bdrv.ensure((size_t)S * NB * 4));
     TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
     uint32_t *bcnt = f->bcnt.as<uint32_t>(), *bdrv = f->bdrv.as<uint32_t>(), *start = f->start_tmp.as<uint32_t>();
+    uint32_t *tot = f->tot.as<uint32_t>();
     CU(cudaMemsetAsync(bdrv, 0, (size_t)S * NB * 4, ctx->st));
-    if (!(f->bucket_valid && f->bucket_N == N)) TRY(fleet_bucketize_async(f, N));
+    CU(cudaMemsetAsync(tot, 0, 2 * tot_words * 4, ctx->st));
+    const bool grouped = f->bucket_valid && f->bucket_N == N && f->geom.n_slabs == g.n_slabs && f->geom.slab == g.slab;
+    if (!grouped) TRY(fleet_bucketize_async(f, N, city->ldc));
     // grouped (from the previous day, a copy of a grouped fleet, or just now): bucket sizes and bucket starts are current
     CU(cudaMemcpyAsync(bcnt, f->cnt_cur.p, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
     Scalars *sc = f->scalars.as<Scalars>();
     BucketArgs a;
     memset(&a, 0, sizeof a);
     a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
+    a.gshift = 32 - ilog2(city->G);
     a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
     a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
-    a.N = N; a.T_tab = city->T; a.C = C; a.slab = slab;
-    a.start = start; a.dr = f->dest.as<uint32_t>(); a.M = f->pos.as<uint32_t>();
+    a.N = N; a.T_tab = city->T; a.C = C; a.slab = g.slab; a.ring = g.ring;
+    a.start = start; a.first_zone = f->first_zone.as<uint32_t>(); a.dr = f->dest.as<uint32_t>(); a.M = f->pos.as<uint2>();
     a.with_time = o->with_time;
     a.rng = make_rng(o->rng, C);
-    a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo; a.lost = &sc->lost;
+    a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo;
     ScatterArgs sa;
     memset(&sa, 0, sizeof sa);
-    sa.NB = NB; sa.dr = a.dr; sa.C = C; sa.slab = slab; sa.M = a.M; sa.start_next = start;
+    sa.NB = NB; sa.dr = a.dr; sa.C = C; sa.slab = g.slab; sa.M = a.M; sa.start_next = start;
+    sa.first_zone_next = f->first_zone.as<uint32_t>();
     for (int64_t s = 0; s < S; ++s) {
         a.step = s; a.hour = s / o->steps_per_hour;
         a.perm_cur = f->perm[f->cur].as<int32_t>();
         a.drv = bdrv + (size_t)s * NB;
+        a.tot = tot + (size_t)(s & 1) * tot_words;
         // events bracket the sampling kernel alone (the dominant kernel); every third launch only, so that the event
         // records do not perturb the back-to-back launch pipeline of the timed region (3 is coprime to 23, 24 and 47:
         // over a few days every hour is sampled equally often)
@@ -767,18 +793,19 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
             CU(cudaStreamWaitEvent(ctx->st, ctx->step_wait[a.hour], 0));   // this hour's std slab is still on its way up
         const bool timed = ctx->profiling && (ctx->prof_tick++ % 3 == 0);
         if (timed) TRY(profile_open(ctx, 1));
-        LAUNCH(ctx, launch_bucket_sample(a, G, ctx->st));
+        LAUNCH(ctx, launch_bucket_sample(a, g, ctx->st));
         if (timed) TRY(profile_close(ctx));
-        uint32_t *cnt_next = bcnt + (size_t)(s + 1) * NB;
-        LAUNCH(ctx, launch_bucket_colscan(a.M, G, NB, cnt_next, ctx->st));
-        sa.cnt_next = cnt_next; sa.perm_cur = a.perm_cur; sa.perm_next = f->perm[f->cur ^ 1].as<int32_t>();
+        sa.tot = a.tot; sa.tot_zero = tot + (size_t)((s + 1) & 1) * tot_words;
+        sa.cnt_next = bcnt + (size_t)(s + 1) * NB;
+        sa.perm_cur = a.perm_cur; sa.perm_next = f->perm[f->cur ^ 1].as<int32_t>();
         sa.zone_out = (s == S - 1) ? f->zone.as<int32_t>() : nullptr;
-        LAUNCH(ctx, launch_bucket_scatter(sa, G, ctx->st));
+        LAUNCH(ctx, launch_bucket_scatter(sa, g, ctx->st));
         f->cur ^= 1;
     }
     CU(cudaMemcpyAsync(f->cnt_cur.p, bcnt + (size_t)S * NB, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
-    LAUNCH(ctx, launch_bucket_export_counts(bcnt, bdrv, (int)N, S, f->counts.as<uint32_t>(), f->counts.as<uint32_t>() + (size_t)N * S, ctx->st));
-    f->bucket_valid = true; f->bucket_N = N; f->zone_valid = true;
+    LAUNCH(ctx, launch_bucket_export_counts(bcnt, bdrv, (int)N, S, f->counts.as<uint32_t>(), f->counts.as<uint32_t>() + (size_t)N * S,
+                                            &sc->lost, ctx->st));
+    f->bucket_valid = true; f->bucket_N = N; f->geom = g; f->zone_valid = true;
     return CPM_OK;
 }
 
@@ -902,7 +929,7 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     // initializestates (main.jl:88) and the grouping of the cars by zone do not depend on the tables: second stream as well
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->aux_st));
     fleet->car_offset = 0; fleet->zone_valid = true; fleet->bucket_valid = false;
-    if (sampler != CPM_SAMPLER_GATHER && city->G > 0 && bucket_supported(N, city->ldc)) TRY(fleet_bucketize_async(fleet, N, ctx->aux_st));
+    if (sampler != CPM_SAMPLER_GATHER && city->G > 0 && bucket_supported(N, city->ldc)) TRY(fleet_bucketize_async(fleet, N, city->ldc, ctx->aux_st));
     CU(cudaEventRecord(ctx->ev_aux[1], ctx->aux_st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev_aux[1], 0));
     cpm_day_opts o;
@@ -1079,7 +1106,7 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
     if (rc == CPM_OK) rc = cpm_fleet_set_zones(base, initial_zones);
     if (rc == CPM_OK && P >= 2) rc = cpm_city_prepare_multi_day(city);   // many days on the same inputs
     // every set starts from the same state: group it by zone once, the per-set copy takes the grouping along
-    if (rc == CPM_OK && P >= 2 && city_alloc_cdf(city) == CPM_OK && city->G > 0 && bucket_supported(N, city->ldc)) rc = fleet_bucketize_async(base, N);
+    if (rc == CPM_OK && P >= 2 && city_alloc_cdf(city) == CPM_OK && city->G > 0 && bucket_supported(N, city->ldc)) rc = fleet_bucketize_async(base, N, city->ldc);
     std::vector<unsigned long long> tc((size_t)T);
     bool have_e_dest = false;
     double cur_e_dest = 0.0;

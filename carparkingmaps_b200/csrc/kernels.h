@@ -63,36 +63,49 @@ int launch_step_gather(const StepArgs &a, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int n, double *out, cudaStream_t st);
 
 // ---- bucket.cu --------------------------------------------------------------------------------
+constexpr int kTotStride = 64;   // uint32 words between two per-destination arrival counters: 256 B, one L2 slice each
+struct BucketGeom {
+    int n_slabs;               // CTAs of k_bucket_sample / k_bucket_scatter (whole waves of one fat CTA per SM)
+    int64_t slab;              // slots per CTA (<= 65,472: ranks are 16-bit)
+    int threads;               // CTA width of both kernels
+    int ring;                  // CDF row buffers per CTA
+    size_t smem_sample, smem_scatter;
+};
 struct BucketArgs {
-    const double *p_drive; const double *cdf; int64_t ldc; int32_t goff, G; const uint8_t *rowzero; const double *dm;
+    const double *p_drive; const double *cdf; int64_t ldc; int32_t goff, G, gshift; const uint8_t *rowzero; const double *dm;
     const double2 *msd;        // nullable: (mean, std) pairs
     int64_t N, T_tab;
     const int32_t *perm_cur;   // [C] car ids grouped by zone bin
     const uint32_t *start;     // [N+2] first slot of every bin (bin N = lost cars), start[N+1] = C
+    const uint32_t *first_zone;// [n_slabs] the bin that holds the first slot of every slab
     uint32_t *dr;              // [C] per slot: destination bin (low 16 bits) | rank among the slab's cars with that destination
-    uint32_t *M;               // [G][N+1] per-slab destination histogram
+    uint2 *M;                  // [n_slabs][N+1] {cars of slab g bound for bin b, where they start inside bucket b}
+    uint32_t *tot;             // [(N+1) * kTotStride] arrivals per destination bin, zero on entry
     int64_t C, slab, step, hour;
-    int32_t with_time;
+    int32_t with_time, ring;
     RngDev rng;
     uint32_t *drv;             // [N+1] driving cars per origin of this step
-    unsigned long long *t_hi, *t_lo, *lost;
+    unsigned long long *t_hi, *t_lo;
 };
 struct ScatterArgs {
-    const uint32_t *cnt_next; int NB;   // new bucket sizes (written by the column scan)
+    int NB;
+    const uint32_t *tot;       // [(N+1) * kTotStride] arrivals of this step
+    uint32_t *tot_zero;        // the counters of the next step but one (zeroed here)
+    uint32_t *cnt_next;        // [N+1] new bucket sizes (= the parked-car histogram of the next step)
     const uint32_t *dr; const int32_t *perm_cur; int32_t *perm_next; int64_t C, slab;
-    const uint32_t *M;         // [G][N+1] exclusive prefix over slabs
+    const uint2 *M;
     uint32_t *start_next;      // [N+2] written by block 0
+    uint32_t *first_zone_next; // [n_slabs]
     int32_t *zone_out;         // nullable: car-id indexed zone (written on the last step of a day)
 };
 bool bucket_supported(int64_t N, int64_t ldc);
-void bucket_grid(int64_t N, int64_t ldc, int64_t C, int *G_out, int64_t *slab_out);
-int launch_bucket_sample(const BucketArgs &a, int G, cudaStream_t st);
-int launch_bucket_colscan(uint32_t *M, int G, int NB, uint32_t *cnt_next, cudaStream_t st);
-int launch_bucket_scatter(const ScatterArgs &a, int G, cudaStream_t st);
+bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g);
+int launch_bucket_sample(const BucketArgs &a, const BucketGeom &g, cudaStream_t st);
+int launch_bucket_scatter(const ScatterArgs &a, const BucketGeom &g, cudaStream_t st);
 int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start, uint32_t *cursor_tmp,
-                     int32_t *perm, cudaStream_t st);
+                     int32_t *perm, uint32_t *first_zone, const BucketGeom &g, cudaStream_t st);
 int launch_bucket_export_counts(const uint32_t *cnt, const uint32_t *drv, int N, int64_t n_steps, uint32_t *parking,
-                                uint32_t *driving, cudaStream_t st);
+                                uint32_t *driving, unsigned long long *lost, cudaStream_t st);
 int launch_finalize_time(unsigned long long *hi, unsigned long long *lo, double *out, cudaStream_t st);
 
 // helpers

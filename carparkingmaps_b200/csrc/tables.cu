@@ -272,22 +272,23 @@ __global__ void __launch_bounds__(256) k_pdest_unnorm(const double *__restrict__
     const int64_t NN = N * N;
     if (idx >= NN) return;
     double v[TMAX > 0 ? TMAX : 1];
-    double mx, mn, nan_probe = 0.0;   // fmax/fmin drop NaN; the running sum keeps it (Julia's maximum/minimum propagate NaN)
+    double mx, mn;
+    bool has_nan = false;   // fmax/fmin drop NaN, Julia's maximum/minimum propagate it (and keep Inf, as fmax/fmin do)
     if constexpr (TMAX > 0) {
 #pragma unroll
         for (int t = 0; t < TMAX; ++t) v[t] = (t < T) ? __ldg(dm + idx + NN * t) : 0.0;
         mx = mn = v[0];
 #pragma unroll
         for (int t = 0; t < TMAX; ++t)
-            if (t < T) { mx = fmax(mx, v[t]); mn = fmin(mn, v[t]); nan_probe += v[t] * 0.0; }
+            if (t < T) { mx = fmax(mx, v[t]); mn = fmin(mn, v[t]); has_nan |= v[t] != v[t]; }
     } else {
         mx = mn = __ldg(dm + idx);
         for (int64_t t = 0; t < T; ++t) {
             const double x = __ldg(dm + idx + NN * t);
-            mx = fmax(mx, x); mn = fmin(mn, x); nan_probe += x * 0.0;
+            mx = fmax(mx, x); mn = fmin(mn, x); has_nan |= x != x;
         }
     }
-    if (nan_probe != nan_probe) mx = mn = __longlong_as_double(0x7ff8000000000000LL);   // NaN or Inf among the inputs
+    if (has_nan) mx = mn = __longlong_as_double(0x7ff8000000000000LL);   // NaN among the inputs
     const bool ok = mx > 0.0;   // :22
     const double den = mx - mn;
     const double rden = 1.0 / den;

@@ -15,19 +15,25 @@ PARAMETER_HEADER = ["T (time steps)", "number_zones", "cars_per_zone", "C (numbe
 
 
 def jl_float(x: float) -> str:
-    """Julia's `string(::Float64)`: shortest digits that round-trip; exponent form `d.ddde-5` outside 1e-5 <= |x| < 1e21."""
+    """Julia's `string(::Float64)` (Ryu `writeshortest`, what CSV.write prints): the shortest digits that round-trip,
+    plain decimals for 1e-4 <= |x| < 1e6 and exponent form `d.ddde6` / `d.ddde-5` outside that range (so 2,357,000 cars
+    are written as `2.357e6`)."""
     x = float(x)
     if x != x:
         return "NaN"
     if x in (float("inf"), float("-inf")):
         return "Inf" if x > 0 else "-Inf"
-    r = repr(x)
-    if "e" in r:
-        mant, exp = r.split("e")
-        if "." not in mant:
-            mant += ".0"
-        return f"{mant}e{int(exp)}"
-    return r   # both languages print plain decimals for 1e-4 <= |x| < 1e16 with the same shortest digits
+    r = repr(x)   # Python's repr is the same shortest round-trip digit string; only the layout differs
+    if "e" not in r and abs(x) < 1e6:
+        return r   # both languages print plain decimals here (Python switches to exponents below 1e-4 as Julia does)
+    from decimal import Decimal
+    sign, digits, exp = Decimal(r).as_tuple()
+    digits = list(digits)
+    while len(digits) > 1 and digits[-1] == 0:
+        digits.pop(); exp += 1
+    e10 = len(digits) + exp - 1
+    mant = str(digits[0]) + "." + ("".join(map(str, digits[1:])) or "0")
+    return f"{'-' if sign else ''}{mant}e{e10}"
 
 
 def createresultsdirectory(path_to_results_folder: str, city: str) -> str:

@@ -67,12 +67,13 @@ def test_device_row_scatter_matches_oracle(ctx, N, density, dup):
 
 def test_julia_float_formatting():
     cases = {1.0: "1.0", 0.5: "0.5", 1e-5: "1.0e-5", 1.5e-7: "1.5e-7", 0.0001: "0.0001", 123456.789: "123456.789",
-             1e21: "1.0e21", 2.5e22: "2.5e22", 0.0: "0.0", -3.25e-9: "-3.25e-9", float("nan"): "NaN", 0.00012: "0.00012",
+             1e21: "1.0e21", 2.5e22: "2.5e22", 0.0: "0.0", 1e6: "1.0e6", 2357000.0: "2.357e6", 1e15: "1.0e15", 999999.5: "999999.5",
+             100000.0: "100000.0", -2400000.0: "-2.4e6", 1234567.891: "1.234567891e6", -3.25e-9: "-3.25e-9", float("nan"): "NaN", 0.00012: "0.00012",
              0.00004166666666666667: "4.1666666666666665e-5" if repr(0.00004166666666666667) == "4.1666666666666665e-05" else None}
     for x, want in cases.items():
         if want is not None:
             assert results_io.jl_float(x) == want, (x, results_io.jl_float(x), want)
-    for x in np.random.default_rng(1).random(200) * 10.0 ** np.random.default_rng(2).integers(-8, 6, 200):
+    for x in np.random.default_rng(1).random(200) * 10.0 ** np.random.default_rng(2).integers(-8, 12, 200):
         assert float(results_io.jl_float(x)) == x             # round-trips
 
 
