@@ -6,7 +6,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcpm.so")
+SO_PATH = os.environ.get("CPM_LIBCPM") or os.path.join(_HERE, "libcpm.so")   # CPM_LIBCPM: a debug build of the same library
 CSRC = os.path.join(_HERE, "csrc")
 
 CPM_OK = 0
@@ -59,6 +59,8 @@ SIGNATURES = {
     "cpm_ctx_profile_end": (_i32, [_vp, C.POINTER(_d), C.POINTER(_i64)]),
     "cpm_host_alloc": (_i32, [_i64, _pp]),
     "cpm_host_free": (_i32, [_vp]),
+    "cpm_host_register": (_i32, [_vp, _i64]),
+    "cpm_host_unregister": (_i32, [_vp]),
     "cpm_create_pdrive": (_i32, [_vp, _vp, _vp, _i64, _i64, _d, _d, _d, _vp]),
     "cpm_create_pdestin": (_i32, [_vp, _vp, _i64, _i64, _d, _vp]),
     "cpm_initialize_states": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
@@ -75,6 +77,7 @@ SIGNATURES = {
     "cpm_city_upload_rows": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, C.POINTER(_i64)]),
     "cpm_city_synth": (_i32, [_vp, _u64, _d]),
     "cpm_city_download_inputs": (_i32, [_vp, _vp, _vp]),
+    "cpm_city_release_tables": (_i32, [_vp]),
     "cpm_city_prepare_multi_day": (_i32, [_vp]),
     "cpm_city_build_pdrive": (_i32, [_vp, _d, _d, _d]),
     "cpm_city_build_pdestin": (_i32, [_vp, _d, _i32]),

@@ -25,6 +25,8 @@
 // Round 1's design (per-CTA histogram rows for 592 CTAs + a column-scan kernel + a sector-per-car scatter, block
 // barriers around a compaction list) is in the history of this file; see profiles/README.md for the measurements.
 // Reference semantics: src/resampling.jl:11-83, src/solveinitialvalueproblem.jl:11-53, src/saveresults.jl:8-17.
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -44,268 +46,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// -DCPM_DEBUG: device-side index checks (printf + trap) for the index arithmetic of the two kernels
+#ifdef CPM_DEBUG
+#define CPM_CHECK(cond, fmt, ...) do { if (!(cond)) { printf("CPM_CHECK %d blk %d tid %d: " fmt "\n", __LINE__, (int)blockIdx.x, (int)threadIdx.x, __VA_ARGS__); __trap(); } } while (0)
+#else
+#define CPM_CHECK(cond, fmt, ...) do { } while (0)
+#endif
+
+// Loads of data the PREVIOUS kernel of the chain wrote (bucket starts, car ids, (destination, rank) words, histogram rows,
+// arrival counters).  Under programmatic dependent launch this kernel's CTAs are resident before that kernel has
+// finished, so such data is not read-only for the lifetime of this kernel: no ld.global.nc (__ldg), L2 is the point
+// of coherence (ld.global.cg).
+template <typename T> __device__ __forceinline__ T ld_prev(const T *p) { return __ldcg(p); }
+
 constexpr int kMaxRing = 8;
 constexpr size_t kSmemCap = 227 * 1024;
-constexpr size_t kSampleTail = 128;      // mbarriers, ring counters, reduction scratch
+constexpr size_t kSampleTail = 320;      // mbarriers, ring state, group counter, reduction / scan scratch
 
 __host__ __device__ inline size_t hist_bytes(int64_t N) { return ((size_t)(N + 1) * 4 + 15) / 16 * 16; }
+__host__ __device__ inline size_t gtab_bytes(int64_t N) { return ((size_t)(N + 2) * 4 + 15) / 16 * 16; }
 
 // ------------------------------------------------------------------------------------------------
-// k_bucket_sample
-// ------------------------------------------------------------------------------------------------
-// Philox4x32-10 words of (car, step, phase); u52() of (o0,o1) and (o2,o3) are the two uniforms of philox_pair()
-__device__ __forceinline__ void philox_words(const RngDev &r, int64_t car, uint32_t step, uint32_t phase, uint32_t (&o)[4])
-{
-    const uint64_t g = (uint64_t)(r.car_offset + car);
-    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), step, r.stream * 2u + phase, r.k0, r.k1, o);
-}
-
-template <int THREADS, int U, bool INJ, bool TIME>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const BucketArgs a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int W = THREADS / 32, GS = 32 * U;
-    const int64_t N = a.N, NN = a.N * a.N;
-    const int Ni = (int)N, NB = Ni + 1;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const int R = a.ring;
-    const uint32_t row_bytes = (uint32_t)(a.ldc * 8);   // CDF row + its guide table: one bulk copy
-    double *const ring = reinterpret_cast<double *>(smem_raw);
-    uint32_t *const hist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)R * row_bytes);   // [N+1] cars of this CTA per destination
-    uint64_t *const full = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(hist) + hist_bytes(N));   // [kMaxRing]
-    uint32_t *const done = reinterpret_cast<uint32_t *>(full + kMaxRing);                                         // [kMaxRing]
-    unsigned long long *const red = reinterpret_cast<unsigned long long *>(done + kMaxRing);                      // [2]
-
-    if (tid == 0) {
-        for (int s = 0; s < R; ++s) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    if (tid < kMaxRing) done[tid] = 0u;
-    if (tid < 2) red[tid] = 0ull;
-    for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(hist)[x] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-    pdl_trigger();
-    pdl_wait();
-
-    const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
-    const double *__restrict__ pd_t = a.p_drive + N * a.hour;
-    const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
-    const int64_t uoff = a.rng.ld * a.step;
-    const uint64_t l2_stream = l2_evict_first_policy();
-    unsigned long long t_hi = 0ull, t_lo = 0ull;
-
-    // this CTA's slab of slots
-    const uint32_t slab_lo = (uint32_t)min((int64_t)blockIdx.x * a.slab, a.C);
-    const uint32_t slab_hi = (uint32_t)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
-
-    // (re-)arm ring buffer `slot` for bin z: a TMA row copy when cars of the slab may search it, a plain arrival otherwise
-    auto issue = [&](int z, int slot) {
-        const uint32_t lo = max(__ldg(a.start + z), slab_lo), hi = min(__ldg(a.start + z + 1), slab_hi);
-        if (z < Ni && lo < hi && rz_t[z] == 0) {
-            fence_proxy_async();   // the buffer's last readers signalled `done` before this
-            mbar_expect_tx(&full[slot], row_bytes);
-            tma_bulk_g2s(ring + (size_t)slot * a.ldc, cdf_t + (int64_t)z * a.ldc, row_bytes, &full[slot], l2_stream);
-        } else mbar_arrive(&full[slot]);
-    };
-
-    if (slab_lo < slab_hi) {
-        const int z0 = (int)__ldg(a.first_zone + blockIdx.x);   // the bin that holds slot slab_lo
-        if (tid == 0)
-            for (int k = 0; k < R; ++k) {
-                const int z = z0 + k;
-                if (z >= NB || __ldg(a.start + z) >= slab_hi) break;
-                issue(z, k);
-            }
-        uint32_t rot = 0;   // groups handed out so far: group j of a zone goes to warp (rot + j) % W
-        int slot = 0;       // ring buffer of bin z0 + k: k % R, in its (k / R)-th use
-        uint32_t phase = 0u;
-        for (int k = 0;; ++k, ++slot) {
-            const int z = z0 + k;
-            if (z >= NB) break;
-            if (slot == R) { slot = 0; phase ^= 1u; }
-            const uint32_t zs = __ldg(a.start + z);
-            if (zs >= slab_hi) break;
-            const uint32_t lo = max(zs, slab_lo), hi = min(__ldg(a.start + z + 1), slab_hi);
-            mbar_wait(&full[slot], phase);   // every lane observes the completion of the row copy
-            if (lo < hi) {
-                const bool is_zone = z < Ni;
-                const double pd = is_zone ? __ldg(pd_t + z) : -1.0;
-                const bool rowzero = is_zone ? (rz_t[z] != 0) : true;
-                const double *row = ring + (size_t)slot * a.ldc;
-                const uint16_t *gd = reinterpret_cast<const uint16_t *>(row + a.goff);
-                const uint32_t ngroups = (hi - lo + GS - 1) / GS;
-                unsigned nd_warp = 0;
-                for (uint32_t j = (uint32_t)(warp + W - (int)(rot % W)) % W; j < ngroups; j += W) {
-                    const uint32_t x = lo + j * GS + lane;
-                    // ---- phase 1: Bernoulli drive decision (src/resampling.jl:11-22) ----
-                    int32_t id[U];
-                    double u2[U];
-                    uint32_t cell[U], m_stay[U];
-                    bool act[U], srch[U], stay[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        act[u] = x + 32 * u < hi;
-                        id[u] = act[u] ? __ldg(a.perm_cur + x + 32 * u) : 0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        bool drive = false;
-                        u2[u] = 0.0; cell[u] = 0u;
-                        if (act[u] && is_zone) {
-                            if (INJ) {
-                                drive = a.rng.u_drive[id[u] + uoff] <= pd;                  // :15 (<=; NaN p_drive parks)
-                                if (drive && !rowzero) u2[u] = a.rng.u_dest[id[u] + uoff];
-                            } else {
-                                uint32_t o[4];
-                                philox_words(a.rng, id[u], (uint32_t)a.step, 0u, o);
-                                drive = u52(o[0], o[1]) <= pd;
-                                u2[u] = u52(o[2], o[3]);
-                                cell[u] = o[3] >> a.gshift;   // floor(u2 * G): the top log2(G) bits of the 52-bit uniform
-                            }
-                        }
-                        srch[u] = drive && !rowzero;
-                        stay[u] = act[u] && !srch[u];                                       // parked, all-zero row (:35-36), or lost (bin N)
-                        nd_warp += __popc(__ballot_sync(0xffffffffu, drive));
-                        m_stay[u] = __ballot_sync(0xffffffffu, stay[u]);
-                    }
-                    // stayers: rank among this CTA's cars bound for the own bin, one shared atomic per group
-                    {
-                        unsigned n_stay = 0;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) n_stay += __popc(m_stay[u]);
-                        uint32_t base = 0;
-                        if (lane == 0 && n_stay) base = atomicAdd(&hist[z], n_stay);
-                        base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            if (stay[u]) a.dr[x + 32 * u] = (uint32_t)z | ((base + __popc(m_stay[u] & lt_mask)) << 16);
-                            base += __popc(m_stay[u]);
-                        }
-                    }
-                    // ---- phase 2: categorical destination from the staged row (src/resampling.jl:26-49): guided lower_bound,
-                    //      then the acceptance test of :40 (u = 0, u above the last entry or a NaN sum -> bin N = lost) ----
-                    int slo[U], shi[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        slo[u] = shi[u] = Ni;
-                        if (srch[u] && u2[u] > 0.0) {
-                            if (INJ && !(u2[u] < 1.0)) slo[u] = gd[a.G];
-                            else {
-                                const uint32_t c = INJ ? (uint32_t)(u2[u] * (double)a.G) : cell[u];
-                                slo[u] = gd[c]; shi[u] = gd[c + 1];
-                            }
-                        }
-                    }
-                    for (;;) {
-                        bool any = false;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) any |= slo[u] < shi[u];
-                        if (!any) break;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {   // branch-free: a finished search re-reads row[slo] (slo <= N lies inside the row block)
-                            const bool open = slo[u] < shi[u];
-                            const int mid = (slo[u] + shi[u]) >> 1;
-                            const bool right = row[mid] < u2[u];                                 // NaN compares false -> goes left
-                            slo[u] = (open && right) ? mid + 1 : slo[u];
-                            shi[u] = (open && !right) ? mid : shi[u];
-                        }
-                    }
-                    int dbin[U];
-                    bool far[U];   // a trip to another zone: travel time from the truncated normal
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        dbin[u] = Ni; far[u] = false;
-                        if (srch[u]) {
-                            const bool hit = slo[u] < Ni && u2[u] <= row[slo[u]];
-                            dbin[u] = hit ? slo[u] : Ni;
-                            const uint32_t rank = atomicAdd(&hist[dbin[u]], 1u);
-                            a.dr[x + 32 * u] = (uint32_t)dbin[u] | (rank << 16);
-                            far[u] = hit && dbin[u] != z;
-                            if (TIME && dbin[u] == z) t_hi += 300ull;                           // :58-59
-                        }
-                    }
-                    // ---- phase 3 (time only: counts mode), src/resampling.jl:53-70 ----
-                    if (TIME) {
-                        double mean[U], sd[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            mean[u] = sd[u] = 0.0;
-                            if (far[u]) {
-                                const int64_t od = (int64_t)z + N * (int64_t)dbin[u];
-                                if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean[u] = ms.x; sd[u] = ms.y; }
-                                else {
-                                    mean[u] = ldg_stream(a.dm + od + NN * a.hour, l2_stream);
-                                    sd[u] = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream);
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < U; ++u)
-                            if (far[u]) {
-                                double u3;
-                                if (INJ) u3 = a.rng.u_time[id[u] + uoff];
-                                else { uint32_t o[4]; philox_words(a.rng, id[u], (uint32_t)a.step, 1u, o); u3 = u52(o[0], o[1]); }
-                                double s = sd[u];
-                                if (s == 0.0) s = 0.1 * mean[u];
-                                fx_add(t_hi, t_lo, truncnormal(mean[u], s, u3));
-                            }
-                    }
-                }
-                rot += ngroups;
-                if (is_zone && lane == 0 && nd_warp) {
-                    atomicAdd(a.drv + z, nd_warp);                                             // src/saveresults.jl:13-15
-                    if (TIME && rowzero) t_hi += 300ull * nd_warp;                             // origin == destination: 5 min (:58-59)
-                }
-            }
-            // this warp is through with bin z; the last warp to say so re-arms the buffer with the bin R further on
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(&done[slot], 1u) == (uint32_t)(W - 1)) {
-                    done[slot] = 0u;
-                    const int zn = z + R;
-                    if (zn < NB && __ldg(a.start + zn) < slab_hi) issue(zn, slot);
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // One global atomic per destination this CTA saw: the return value is where this CTA's cars start inside the
-    // destination's bucket.  The counters are one per 256 bytes (one L2 slice each: profiles/r2 micro-benchmark C).
-    {
-        uint2 *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
-        constexpr int B = 4;
-        for (int b0 = tid; b0 < NB; b0 += B * THREADS) {
-            uint32_t h[B], gb[B];
-#pragma unroll
-            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; h[q] = b < NB ? hist[b] : 0u; }
-#pragma unroll
-            for (int q = 0; q < B; ++q) gb[q] = h[q] ? atomicAdd(a.tot + (size_t)(b0 + q * THREADS) * kTotStride, h[q]) : 0u;
-#pragma unroll
-            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; if (b < NB) Mrow[b] = make_uint2(h[q], gb[q]); }
-        }
-    }
-
-    // driving-time total: integer block reduction, two global atomics per CTA
-    if (TIME) {
-        t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo);
-        if (lane == 0) {
-            if (t_hi) atomicAdd(&red[0], t_hi);
-            if (t_lo) atomicAdd(&red[1], t_lo);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
-            if (hi) atomicAdd(a.t_hi, hi);
-            if (lo32) atomicAdd(a.t_lo, lo32);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// exclusive block scans in place (arrays in shared memory); blockDim.x <= 1024
+// exclusive block scan in place (array in shared memory); blockDim.x <= 1024
 // ------------------------------------------------------------------------------------------------
 __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot /*[33]*/)
 {
@@ -340,6 +102,321 @@ __device__ uint32_t block_exclusive_scan(uint32_t *v, int n, uint32_t *warp_tot 
     return warp_tot[32];
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_bucket_sample
+// ------------------------------------------------------------------------------------------------
+// Shared memory: ring of R CDF row blocks | hist[N+1] | gtab[N+2] | tail (mbarriers, ring state, scratch).
+//   gtab[k]   first group of the k-th bin of the slab (bins z0, z0+1, ...; a group = 32*U consecutive slots of one bin)
+//   ring slot of bin ordinal k: k % R in its (k / R)-th use.  full[slot] (mbarrier, one arrival per use) completes when
+//   the row has landed (or at once for a bin nobody searches); gen[slot] is the use the slot is armed for; zdone[slot]
+//   counts the finished groups of that use -- the warp that finishes the last one re-arms the slot for bin k + R.
+struct SampleTail {
+    uint64_t full[kMaxRing];
+    uint32_t zdone[kMaxRing];
+    uint32_t gen[kMaxRing];
+    unsigned long long red[2];
+    uint32_t next_group, pad;
+    uint32_t wt[34];
+};
+static_assert(sizeof(SampleTail) <= kSampleTail, "tail too small");
+
+template <int THREADS, int U, bool INJ, bool TIME>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const BucketArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int GS = 32 * U;
+    const int64_t N = a.N, NN = a.N * a.N;
+    const int Ni = (int)N, NB = Ni + 1;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int R = a.ring, rmask = R - 1, rshift = a.ring_shift;   // R is a power of two
+    const uint32_t row_bytes = (uint32_t)(a.ldc * 8);   // CDF row + its guide table: one bulk copy
+    double *const ring = reinterpret_cast<double *>(smem_raw);
+    uint32_t *const hist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)R * row_bytes);   // [N+1] cars of this CTA per destination
+    uint32_t *const gtab = hist + hist_bytes(N) / 4;                                         // [N+2]
+    SampleTail *const tl = reinterpret_cast<SampleTail *>(reinterpret_cast<unsigned char *>(gtab) + gtab_bytes(N));
+
+    if (tid == 0) {
+        for (int s = 0; s < R; ++s) mbar_init(&tl->full[s], 1);
+        fence_mbar_init();
+        tl->next_group = 0u;
+    }
+    if (tid < kMaxRing) { tl->zdone[tid] = 0u; tl->gen[tid] = 0u; }
+    if (tid < 2) tl->red[tid] = 0ull;
+    for (int x = tid; x < (int)(hist_bytes(N) / 16); x += THREADS) reinterpret_cast<uint4 *>(hist)[x] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    pdl_trigger();
+    pdl_wait();
+
+    const double *__restrict__ cdf_t = a.cdf + a.hour * N * a.ldc;
+    const double *__restrict__ pd_t = a.p_drive + N * a.hour;
+    const uint8_t *__restrict__ rz_t = a.rowzero + a.hour * N;
+    const int64_t uoff = a.rng.ld * a.step;
+    const uint64_t l2_stream = l2_evict_first_policy();
+    unsigned long long t_hi = 0ull, t_lo = 0ull;
+
+    // this CTA's slab of slots, and the bins it covers
+    const uint32_t slab_lo = (uint32_t)min((int64_t)blockIdx.x * a.slab, a.C);
+    const uint32_t slab_hi = (uint32_t)min((int64_t)(blockIdx.x + 1) * a.slab, a.C);
+    const int z0 = (slab_lo < slab_hi) ? (int)ld_prev(a.first_zone + blockIdx.x) : NB;   // the bin that holds slot slab_lo
+    int nz = 0;
+    for (int base = 0;; base += THREADS) {   // usually one trip: a slab covers ~N / #slabs bins
+        const int t = base + tid, z = z0 + t;
+        uint32_t ng = 0;
+        bool valid = false;
+        if (z < NB) {
+            const uint32_t zs = ld_prev(a.start + z);
+            if (zs < slab_hi) {
+                valid = true;
+                const uint32_t lo = max(zs, slab_lo), hi = min(ld_prev(a.start + z + 1), slab_hi);
+                ng = (hi - lo + GS - 1) / GS;
+            }
+        }
+        if (t <= NB) gtab[t] = ng;
+        const int c = __syncthreads_count(valid);
+        nz += c;
+        if (c < THREADS) break;
+    }
+    const uint32_t n_groups = block_exclusive_scan(gtab, nz, tl->wt);
+    if (tid == 0) gtab[nz] = n_groups;
+
+    // (re-)arm ring slot `s` for the next bin of its sequence (ordinals kk, kk + R, ...) that has cars: a TMA row copy when
+    // its cars may search the row, a plain arrival otherwise; bins without cars complete their use at once
+    auto arm = [&](int s, int kk) {
+        for (; kk < nz; kk += R) {
+            if (gtab[kk + 1] == gtab[kk]) { mbar_arrive(&tl->full[s]); continue; }
+            const int z = z0 + kk;
+            if (z < Ni && rz_t[z] == 0) {
+                fence_proxy_async();   // the buffer's last readers finished their groups before this
+                mbar_expect_tx(&tl->full[s], row_bytes);
+                tma_bulk_g2s(ring + (size_t)s * a.ldc, cdf_t + (int64_t)z * a.ldc, row_bytes, &tl->full[s], l2_stream);
+            } else mbar_arrive(&tl->full[s]);
+            break;
+        }
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t *>(&tl->gen[s]) = (uint32_t)(kk >> rshift);
+    };
+    __syncthreads();
+    if (tid < R) arm(tid, tid);
+    __syncthreads();
+
+    // groups are handed out in order through a shared counter; a warp fetches its next group while it works on one
+    auto grab = [&]() {
+        uint32_t g = 0;
+        if (lane == 0) g = atomicAdd(&tl->next_group, 1u);
+        return __shfl_sync(0xffffffffu, g, 0);
+    };
+    int k = 0;
+    for (uint32_t g = grab(); g < n_groups;) {
+        const uint32_t g_next = grab();
+        while (g >= gtab[k + 1]) { ++k; CPM_CHECK(k < nz, "g %u k %d nz %d n_groups %u", g, k, nz, n_groups); }
+        const int z = z0 + k;
+        CPM_CHECK(z < NB, "z %d", z);
+        const uint32_t lo = max(ld_prev(a.start + z), slab_lo), hi = min(ld_prev(a.start + z + 1), slab_hi);
+        const uint32_t x = lo + (g - gtab[k]) * GS + lane;
+        int32_t id[U];
+        bool act[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            act[u] = x + 32 * u < hi;
+            CPM_CHECK(hi <= slab_hi && lo >= slab_lo && lo < hi, "lo %u hi %u slab %u %u z %d k %d g %u", lo, hi, slab_lo, slab_hi, z, k, g);
+            id[u] = act[u] ? ld_prev(a.perm_cur + x + 32 * u) : 0;
+        }
+        const bool is_zone = z < Ni;
+        const double pd = is_zone ? __ldg(pd_t + z) : -1.0;
+        const bool rowzero = is_zone ? (rz_t[z] != 0) : true;
+        const int slot = k & rmask;
+        const uint32_t use = (uint32_t)(k >> rshift);
+        // ---- phase 1: Bernoulli drive decision (src/resampling.jl:11-22) ----
+        double u2[U];
+        uint32_t cell[U], m_stay[U];
+        bool srch[U], stay[U];
+        unsigned nd = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            bool drive = false;
+            u2[u] = 0.0; cell[u] = 0u;
+            if (act[u] && is_zone) {
+                if (INJ) {
+                    drive = a.rng.u_drive[id[u] + uoff] <= pd;                  // :15 (<=; NaN p_drive parks)
+                    if (drive && !rowzero) u2[u] = a.rng.u_dest[id[u] + uoff];
+                } else {
+                    uint32_t o[4];
+                    philox_words(a.rng, id[u], (uint32_t)a.step, 0u, o);
+                    drive = u52(o[0], o[1]) <= pd;
+                    u2[u] = u52(o[2], o[3]);
+                    cell[u] = o[3] >> a.gshift;   // floor(u2 * G): the top log2(G) bits of the 52-bit uniform
+                }
+            }
+            srch[u] = drive && !rowzero;
+            stay[u] = act[u] && !srch[u];                                       // parked, all-zero row (:35-36), or lost (bin N)
+            nd += __popc(__ballot_sync(0xffffffffu, drive));
+            m_stay[u] = __ballot_sync(0xffffffffu, stay[u]);
+        }
+        // stayers: rank among this CTA's cars bound for the own bin, one shared atomic per group
+        {
+            unsigned n_stay = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) n_stay += __popc(m_stay[u]);
+            uint32_t base = 0;
+            if (lane == 0) {
+                if (n_stay) base = atomicAdd(&hist[z], n_stay);
+                if (is_zone && nd) atomicAdd(a.drv + z, nd);                    // src/saveresults.jl:13-15
+            }
+            base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (stay[u]) a.dr[x + 32 * u] = (uint32_t)z | ((base + __popc(m_stay[u] & lt_mask)) << 16);
+                base += __popc(m_stay[u]);
+            }
+            if (TIME && rowzero && is_zone && lane == 0) t_hi += 300ull * nd;   // origin == destination: 5 min (:58-59)
+        }
+        // ---- phase 2: categorical destination from the staged row (src/resampling.jl:26-49): guided lower_bound,
+        //      then the acceptance test of :40 (u = 0, u above the last entry or a NaN sum -> bin N = lost) ----
+        bool any_srch = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) any_srch |= srch[u];
+        if (__any_sync(0xffffffffu, any_srch)) {
+            while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }   // the slot still serves an earlier bin (rare)
+            mbar_wait(&tl->full[slot], use & 1u);   // every lane observes the completion of the row copy
+            const double *row = ring + (size_t)slot * a.ldc;
+            const uint16_t *gd = reinterpret_cast<const uint16_t *>(row + a.goff);
+            int slo[U], shi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                slo[u] = shi[u] = Ni;
+                if (srch[u] && u2[u] > 0.0) {
+                    if (INJ && !(u2[u] < 1.0)) slo[u] = gd[a.G];
+                    else {
+                        const uint32_t c = INJ ? (uint32_t)(u2[u] * (double)a.G) : cell[u];
+                        CPM_CHECK(c < (uint32_t)a.G, "cell %u", c);
+                        slo[u] = gd[c]; shi[u] = gd[c + 1];
+                    }
+                }
+            }
+            for (;;) {
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) any |= slo[u] < shi[u];
+                if (!any) break;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {   // branch-free: a finished search re-reads row[slo] (slo <= N lies inside the row block)
+                    const bool open = slo[u] < shi[u];
+                    const int mid = (slo[u] + shi[u]) >> 1;
+                    const bool right = row[mid] < u2[u];                                 // NaN compares false -> goes left
+                    slo[u] = (open && right) ? mid + 1 : slo[u];
+                    shi[u] = (open && !right) ? mid : shi[u];
+                }
+            }
+            int dbin[U];
+            bool far[U];   // a trip to another zone: travel time from the truncated normal
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                dbin[u] = Ni; far[u] = false;
+                if (srch[u]) {
+                    const bool hit = slo[u] < Ni && u2[u] <= row[slo[u]];
+                    dbin[u] = hit ? slo[u] : Ni;
+                    CPM_CHECK(dbin[u] >= 0 && dbin[u] <= Ni, "dbin %d slo %d shi %d", dbin[u], slo[u], shi[u]);
+                    const uint32_t rank = atomicAdd(&hist[dbin[u]], 1u);
+                    a.dr[x + 32 * u] = (uint32_t)dbin[u] | (rank << 16);
+                    far[u] = hit && dbin[u] != z;
+                    if (TIME && dbin[u] == z) t_hi += 300ull;                           // :58-59
+                }
+            }
+            // ---- phase 3 (time only: counts mode), src/resampling.jl:53-70 ----
+            if (TIME) {
+                double mean[U], sd[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    mean[u] = sd[u] = 0.0;
+                    if (far[u]) {
+                        const int64_t od = (int64_t)z + N * (int64_t)dbin[u];
+                        if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean[u] = ms.x; sd[u] = ms.y; }
+                        else if (a.gather_policy) {
+                            mean[u] = ldg_stream(a.dm + od + NN * a.hour, l2_stream);
+                            sd[u] = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream);
+                        } else {   // default policy: the 32-byte sector also holds the entries of the three neighbouring origins
+                            mean[u] = __ldg(a.dm + od + NN * a.hour);
+                            sd[u] = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (far[u]) {
+                        double u3;
+                        if (INJ) u3 = a.rng.u_time[id[u] + uoff];
+                        else { uint32_t o[4]; philox_words(a.rng, id[u], (uint32_t)a.step, 1u, o); u3 = u52(o[0], o[1]); }
+                        double s = sd[u];
+                        if (s == 0.0) s = 0.1 * mean[u];
+                        fx_add(t_hi, t_lo, truncnormal(mean[u], s, u3));
+                    }
+            }
+        }
+        // this group is done with the row; the warp that finishes the bin's last group re-arms the slot
+        __syncwarp();
+        if (lane == 0) {
+            // zdone[slot] counts one use at a time: a group that never searched may get here while the slot still serves an
+            // earlier bin (rare) and has to wait for its own use before it reports in
+            while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }
+            __threadfence_block();
+            if (atomicAdd(&tl->zdone[slot], 1u) + 1u == gtab[k + 1] - gtab[k]) {
+                mbar_wait(&tl->full[slot], use & 1u);   // nobody may have waited for this bin's row: it must have landed before the
+                tl->zdone[slot] = 0u;                   // buffer and its barrier are armed again
+                arm(slot, k + R);
+            }
+        }
+        g = g_next;
+    }
+    __syncthreads();
+
+#ifdef CPM_DEBUG
+    {   // every slot of the slab must have been ranked exactly once
+        __shared__ unsigned dbg_sum;
+        if (tid == 0) dbg_sum = 0;
+        __syncthreads();
+        unsigned part = 0;
+        for (int b = tid; b < NB; b += THREADS) part += hist[b];
+        atomicAdd(&dbg_sum, part);
+        __syncthreads();
+        if (tid == 0) CPM_CHECK(dbg_sum == slab_hi - slab_lo, "ranked %u slots of %u; z0 %d nz %d n_groups %u ring %d", dbg_sum, slab_hi - slab_lo, z0, nz, n_groups, R);
+    }
+#endif
+    // One global atomic per destination this CTA saw: the return value is where this CTA's cars start inside the
+    // destination's bucket.  The counters are one per 256 bytes (one L2 slice each: profiles/r2 micro-benchmark C).
+    {
+        uint2 *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
+        constexpr int B = 4;
+        for (int b0 = tid; b0 < NB; b0 += B * THREADS) {
+            uint32_t h[B], gb[B];
+#pragma unroll
+            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; h[q] = b < NB ? hist[b] : 0u; }
+#pragma unroll
+            for (int q = 0; q < B; ++q) gb[q] = h[q] ? atomicAdd(a.tot + (size_t)(b0 + q * THREADS) * kTotStride, h[q]) : 0u;
+#pragma unroll
+            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; if (b < NB) Mrow[b] = make_uint2(h[q], gb[q]); }
+        }
+    }
+
+    // driving-time total: integer block reduction, two global atomics per CTA
+    if (TIME) {
+        t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo);
+        if (lane == 0) {
+            if (t_hi) atomicAdd(&tl->red[0], t_hi);
+            if (t_lo) atomicAdd(&tl->red[1], t_lo);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long hi = tl->red[0] + (tl->red[1] >> 32), lo32 = tl->red[1] & 0xffffffffull;
+            if (hi) atomicAdd(a.t_hi, hi);
+            if (lo32) atomicAdd(a.t_lo, lo32);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive block scan of two arrays at once
+// ------------------------------------------------------------------------------------------------
 // two arrays at once (one pass of shuffles and barriers); returns the total of v2
 __device__ uint32_t block_exclusive_scan2(uint32_t *v1, uint32_t *v2, int n, uint32_t *wt /*[66]*/)
 {
@@ -417,12 +494,24 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(cons
 #pragma unroll
     for (int u = 0; u < PS; ++u) {
         const int sl = lo + u * THREADS + tid;
-        v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
-        id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
+        v[u] = (sl < hi) ? ld_prev(dr + sl) : 0u;
+        id[u] = (sl < hi) ? ld_prev(pc + sl) : 0;
     }
-    for (int x = tid; x < NB; x += THREADS) {
-        lstart[x] = __ldg(&Mrow[x].x);
-        off[x] = __ldg(a.tot + (size_t)x * kTotStride);
+    constexpr int MQ = 4;      // bins per thread held in registers across the scan (more bins: re-read below)
+    uint32_t gbq[MQ];
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) {
+        const int x = tid + q * THREADS;
+        gbq[q] = 0u;
+        if (x < NB) {
+            const uint2 m = ld_prev(&Mrow[x]);
+            lstart[x] = m.x; gbq[q] = m.y;
+            off[x] = ld_prev(a.tot + (size_t)x * kTotStride);
+        }
+    }
+    for (int x = tid + MQ * THREADS; x < NB; x += THREADS) {
+        lstart[x] = ld_prev(&Mrow[x].x);
+        off[x] = ld_prev(a.tot + (size_t)x * kTotStride);
     }
     __syncthreads();
     const uint32_t total = block_exclusive_scan2(lstart, off, NB, wt);
@@ -434,9 +523,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(cons
         }
         if (tid == 0) a.start_next[NB] = total;
     }
-    if (tid == 0) a.first_zone_next[blockIdx.x] = (uint32_t)bin_of_slot(off, NB, (uint32_t)lo);
+    // the bin that holds this slab's first slot at the next step: the largest z with start[z] <= lo
+    for (int x = tid; x < NB; x += THREADS)
+        if (off[x] <= (uint32_t)lo && (x + 1 == NB || off[x + 1] > (uint32_t)lo)) a.first_zone_next[blockIdx.x] = (uint32_t)x;
     __syncthreads();
-    for (int x = tid; x < NB; x += THREADS) off[x] += __ldg(&Mrow[x].y) - lstart[x];
+#pragma unroll
+    for (int q = 0; q < MQ; ++q) { const int x = tid + q * THREADS; if (x < NB) off[x] += gbq[q] - lstart[x]; }
+    for (int x = tid + MQ * THREADS; x < NB; x += THREADS) off[x] += ld_prev(&Mrow[x].y) - lstart[x];
     __syncthreads();
     // pass 1: sort the slab by destination in shared memory
     for (int s0 = lo; s0 < hi; s0 += PS * THREADS) {
@@ -444,8 +537,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(cons
 #pragma unroll
             for (int u = 0; u < PS; ++u) {
                 const int sl = s0 + u * THREADS + tid;
-                v[u] = (sl < hi) ? __ldg(dr + sl) : 0u;
-                id[u] = (sl < hi) ? __ldg(pc + sl) : 0;
+                v[u] = (sl < hi) ? ld_prev(dr + sl) : 0u;
+                id[u] = (sl < hi) ? ld_prev(pc + sl) : 0;
             }
         }
 #pragma unroll
@@ -453,6 +546,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(cons
             const int sl = s0 + u * THREADS + tid;
             if (sl < hi) {
                 const uint32_t d = v[u] & 0xffffu, p = lstart[d] + (v[u] >> 16);
+                CPM_CHECK(d < (uint32_t)NB && p < (uint32_t)(hi - lo), "slot %d d %u rank %u p %u n %d", sl, d, v[u] >> 16, p, hi - lo);
                 sid[p] = id[u];
                 sdst[p] = (uint16_t)d;
             }
@@ -464,6 +558,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(cons
     for (int p = tid; p < n; p += THREADS) {
         const uint32_t d = sdst[p];
         const int32_t car = sid[p];
+        CPM_CHECK(off[d] + (uint32_t)p < (uint32_t)a.C, "p %d d %u pos %u", p, d, off[d] + (uint32_t)p);
         a.perm_next[off[d] + (uint32_t)p] = car;
         if (a.zone_out) a.zone_out[car] = (d < (uint32_t)(NB - 1)) ? (int32_t)d + 1 : 0;   // last step: car-id indexed state
     }
@@ -572,11 +667,12 @@ bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g)
     const int threads = env_int("CPM_BUCKET_THREADS", 1024) == 512 ? 512 : 1024;
     const int per_sm = 1024 / threads;
     const size_t cap = kSmemCap / per_sm - (per_sm > 1 ? 1024 : 0);
-    const size_t fixed1 = hist_bytes(N) + kSampleTail, row = (size_t)ldc * 8;
+    const size_t fixed1 = hist_bytes(N) + gtab_bytes(N) + kSampleTail, row = (size_t)ldc * 8;
     if (fixed1 + row > cap) return false;
     int ring = (int)std::min<size_t>(kMaxRing, (cap - fixed1) / row);
     const int ring_env = env_int("CPM_BUCKET_RING", 0);
     if (ring_env >= 1 && ring_env < ring) ring = ring_env;
+    while (ring & (ring - 1)) ring &= ring - 1;   // a power of two: slot and use of a bin are a mask and a shift
     const size_t fixed2 = scatter_smem(NB, 0) + 64;
     if (fixed2 + 6 * 256 > cap) return false;
     int64_t slab_cap = (int64_t)((cap - fixed2) / 6) & ~(int64_t)63;

@@ -3,6 +3,7 @@
 // No CPU fallback: every computing entry point launches the sm_100a kernels or fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -265,6 +266,21 @@ extern "C" int32_t cpm_host_free(void *p)
     return CPM_OK;
 }
 
+// Page-locks an EXISTING host array (e.g. a Julia Array) for the duration of a batch of calls, so that the uploads of
+// the host-pointer entry points run at full PCIe rate and overlap with the kernels; undo with cpm_host_unregister.
+extern "C" int32_t cpm_host_register(void *p, int64_t bytes)
+{
+    ARG(p != nullptr && bytes > 0);
+    CU(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+    return CPM_OK;
+}
+extern "C" int32_t cpm_host_unregister(void *p)
+{
+    ARG(p != nullptr);
+    CU(cudaHostUnregister(p));
+    return CPM_OK;
+}
+
 extern "C" int32_t cpm_ctx_profile_begin(cpm_ctx *ctx)
 {
     TRY(use(ctx));
@@ -326,6 +342,20 @@ extern "C" int32_t cpm_city_destroy(cpm_city *c)
     c->dm.release(); c->dist.release(); c->rdist.release(); c->msd.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
     c->norm.release(); c->cdf.release(); c->rowzero.release();
     delete c;
+    return CPM_OK;
+}
+
+// Drops the tables (p_drive, p_dest, CDF, pair table, scratch) and keeps the inputs: the blocks go back to the device's
+// free list, where the next city of a batch finds them (BASELINE configs[2]: 34 cities resident, one set of tables).
+extern "C" int32_t cpm_city_release_tables(cpm_city *c)
+{
+    ARG(c != nullptr);
+    TRY(use(c->ctx));
+    if (c->ctx->aux_st) CU(cudaStreamSynchronize(c->ctx->aux_st));
+    CU(cudaStreamSynchronize(c->ctx->st));
+    c->rdist.release(); c->msd.release(); c->mean_sum.release(); c->p_drive.release(); c->p_dest.release();
+    c->norm.release(); c->cdf.release(); c->rowzero.release();
+    c->have_meansum = c->have_pdrive = c->have_cdf = c->have_pdest = c->have_msd = false;
     return CPM_OK;
 }
 
@@ -659,6 +689,7 @@ static RngDev make_rng(const cpm_rng &r, int64_t C)
     d.car_offset = r.car_offset;
     d.ld = C;
     d.u_drive = r.u_drive; d.u_dest = r.u_dest; d.u_time = r.u_time; d.u_dist = r.u_dist;
+    for (uint32_t i = 0; i < 10; ++i) { d.rk0[i] = d.k0 + i * 0x9E3779B9u; d.rk1[i] = d.k1 + i * 0xBB67AE85u; }
     return d;
 }
 
@@ -772,7 +803,8 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     a.gshift = 32 - ilog2(city->G);
     a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
     a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
-    a.N = N; a.T_tab = city->T; a.C = C; a.slab = g.slab; a.ring = g.ring;
+    a.N = N; a.T_tab = city->T; a.C = C; a.slab = g.slab; a.ring = g.ring; a.ring_shift = ilog2(g.ring);
+    { static const int gp = getenv("CPM_GATHER_EVICT_FIRST") ? atoi(getenv("CPM_GATHER_EVICT_FIRST")) : 0; a.gather_policy = gp; }
     a.start = start; a.first_zone = f->first_zone.as<uint32_t>(); a.dr = f->dest.as<uint32_t>(); a.M = f->pos.as<uint2>();
     a.with_time = o->with_time;
     a.rng = make_rng(o->rng, C);

@@ -82,7 +82,7 @@ struct BucketArgs {
     uint2 *M;                  // [n_slabs][N+1] {cars of slab g bound for bin b, where they start inside bucket b}
     uint32_t *tot;             // [(N+1) * kTotStride] arrivals per destination bin, zero on entry
     int64_t C, slab, step, hour;
-    int32_t with_time, ring;
+    int32_t with_time, ring, ring_shift, gather_policy;   // gather_policy 1: L2 evict-first on the travel-time gathers
     RngDev rng;
     uint32_t *drv;             // [N+1] driving cars per origin of this step
     unsigned long long *t_hi, *t_lo;

@@ -135,6 +135,11 @@ class City:
         L.check(L.lib().cpm_city_download_inputs(self._h, _ptr(dm), _ptr(dist)))
         return dm, dist
 
+    def release_tables(self):
+        """Free the tables (their device blocks are recycled); the inputs stay resident."""
+        L.check(L.lib().cpm_city_release_tables(self._h))
+        return self
+
     def prepare_multi_day(self):
         """Build the (mean, std) pair table: halves the travel-time gather traffic of every later resampling day."""
         L.check(L.lib().cpm_city_prepare_multi_day(self._h))

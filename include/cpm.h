@@ -85,6 +85,10 @@ int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int64_t *step_
 /* pinned host memory for callers that want full-rate PCIe copies */
 int32_t cpm_host_alloc(int64_t bytes, void **out);
 int32_t cpm_host_free(void *p);
+/* page-lock / unlock a host array the caller already owns (a Julia Array, a numpy array): uploads from registered
+ * memory run at full PCIe rate and overlap with the kernels, like memory from cpm_host_alloc */
+int32_t cpm_host_register(void *p, int64_t bytes);
+int32_t cpm_host_unregister(void *p);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Host API: one entry per reference function (HOST pointers, synchronous)                  */
@@ -166,6 +170,8 @@ int32_t cpm_city_upload_rows(cpm_city *city, const int32_t *sourceid, const int3
                              const double *distance_matrix_km, int64_t *n_skipped);
 int32_t cpm_city_synth(cpm_city *city, uint64_t seed, double density);
 int32_t cpm_city_download_inputs(cpm_city *city, double *datamatrix, double *distance_matrix_km);
+/* frees the tables and scratch of a city (inputs stay resident); their device blocks are recycled by the next build */
+int32_t cpm_city_release_tables(cpm_city *city);
 /* optional: build the (mean, std) pair table that halves the travel-time gather traffic; pays off when many days are
  * sampled on the same inputs (cpm_sweep calls it itself) */
 int32_t cpm_city_prepare_multi_day(cpm_city *city);
