@@ -65,6 +65,7 @@ constexpr size_t kSampleTail = 320;      // mbarriers, ring state, group counter
 
 __host__ __device__ inline size_t hist_bytes(int64_t N) { return ((size_t)(N + 1) * 4 + 15) / 16 * 16; }
 __host__ __device__ inline size_t gtab_bytes(int64_t N) { return ((size_t)(N + 2) * 4 + 15) / 16 * 16; }
+__host__ __device__ inline size_t zlo_bytes(int64_t N) { return ((size_t)(N + 2) * 2 + 15) / 16 * 16; }
 
 // ------------------------------------------------------------------------------------------------
 // exclusive block scan in place (array in shared memory); blockDim.x <= 1024
@@ -120,12 +121,44 @@ struct SampleTail {
 };
 static_assert(sizeof(SampleTail) <= kSampleTail, "tail too small");
 
+// one entry of a warp's travel-time queue: a car that drives to another zone (src/resampling.jl:61-70)
+struct FarCar { int32_t id; uint32_t od; };   // od = origin | destination << 16
+constexpr int kFarQueue = 128;                 // entries per warp (a power of two, >= 32 * U + 31)
+
+// travel-time draws of up to 32 queued cars, one per lane: (mean, std) gathered from datamatrix, second Philox call,
+// inverse-CDF truncated normal, fixed-point sum.  Dense lanes whatever the share of drivers in the groups was.
+template <bool INJ>
+__device__ __forceinline__ void far_batch(const BucketArgs &a, const FarCar *q, uint32_t head, int n, int lane, int64_t uoff,
+                                          uint64_t l2_stream, unsigned long long &t_hi, unsigned long long &t_lo)
+{
+    if (lane < n) {
+        const FarCar e = q[(head + lane) & (kFarQueue - 1)];
+        const int64_t N = a.N, NN = a.N * a.N;
+        const int64_t od = (int64_t)(e.od & 0xffffu) + N * (int64_t)(e.od >> 16);
+        double mean, sd;
+        if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean = ms.x; sd = ms.y; }
+        else if (a.gather_policy) {
+            mean = ldg_stream(a.dm + od + NN * a.hour, l2_stream);
+            sd = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream);
+        } else {
+            mean = __ldg(a.dm + od + NN * a.hour);
+            sd = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
+        }
+        double u3;
+        if (INJ) u3 = a.rng.u_time[e.id + uoff];
+        else { uint32_t o[4]; philox_words(a.rng, e.id, (uint32_t)a.step, 1u, o); u3 = u52(o[0], o[1]); }
+        if (sd == 0.0) sd = 0.1 * mean;                                   // :65-67
+        fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));                    // :68
+    }
+}
+
 template <int THREADS, int U, bool INJ, bool TIME>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const BucketArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int GS = 32 * U;
-    const int64_t N = a.N, NN = a.N * a.N;
+    constexpr int GS = 32 * U, W = THREADS / 32;
+    static_assert(!TIME || GS + 31 <= kFarQueue, "travel-time queue too small for this group size");
+    const int64_t N = a.N;
     const int Ni = (int)N, NB = Ni + 1;
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -133,8 +166,10 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
     const uint32_t row_bytes = (uint32_t)(a.ldc * 8);   // CDF row + its guide table: one bulk copy
     double *const ring = reinterpret_cast<double *>(smem_raw);
     uint32_t *const hist = reinterpret_cast<uint32_t *>(smem_raw + (size_t)R * row_bytes);   // [N+1] cars of this CTA per destination
-    uint32_t *const gtab = hist + hist_bytes(N) / 4;                                         // [N+2]
-    SampleTail *const tl = reinterpret_cast<SampleTail *>(reinterpret_cast<unsigned char *>(gtab) + gtab_bytes(N));
+    uint32_t *const gtab = hist + hist_bytes(N) / 4;                                         // [N+2] first group of every bin of the slab
+    uint16_t *const zlo = reinterpret_cast<uint16_t *>(gtab + gtab_bytes(N) / 4);            // [N+2] first slot of every bin, relative to slab_lo
+    SampleTail *const tl = reinterpret_cast<SampleTail *>(reinterpret_cast<unsigned char *>(zlo) + zlo_bytes(N));
+    FarCar *const farq = reinterpret_cast<FarCar *>(reinterpret_cast<unsigned char *>(tl) + kSampleTail) + (size_t)(tid >> 5) * kFarQueue;   // TIME only
 
     if (tid == 0) {
         for (int s = 0; s < R; ++s) mbar_init(&tl->full[s], 1);
@@ -162,17 +197,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
     int nz = 0;
     for (int base = 0;; base += THREADS) {   // usually one trip: a slab covers ~N / #slabs bins
         const int t = base + tid, z = z0 + t;
-        uint32_t ng = 0;
+        uint32_t ng = 0, lo = slab_hi;
         bool valid = false;
         if (z < NB) {
             const uint32_t zs = ld_prev(a.start + z);
             if (zs < slab_hi) {
                 valid = true;
-                const uint32_t lo = max(zs, slab_lo), hi = min(ld_prev(a.start + z + 1), slab_hi);
+                lo = max(zs, slab_lo);
+                const uint32_t hi = min(ld_prev(a.start + z + 1), slab_hi);
                 ng = (hi - lo + GS - 1) / GS;
             }
         }
-        if (t <= NB) gtab[t] = ng;
+        if (t <= NB) { gtab[t] = ng; zlo[t] = (uint16_t)(lo - slab_lo); }   // the first bin past the slab gets slab_hi: zlo[k + 1] closes bin k
         const int c = __syncthreads_count(valid);
         nz += c;
         if (c < THREADS) break;
@@ -200,49 +236,54 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
     if (tid < R) arm(tid, tid);
     __syncthreads();
 
-    // groups are handed out in order through a shared counter; a warp fetches its next group while it works on one
-    auto grab = [&]() {
+    // Groups are handed out in order through a shared counter.  A warp is always one group ahead: while it works on a
+    // group it already holds the next one's number, bin and car ids (their L2 latency hides behind the current group).
+    int k = 0;                 // bin ordinal cursor of this warp (groups come in increasing order)
+    uint32_t q_head = 0u;      // travel-time queue of this warp (TIME)
+    int q_cnt = 0;
+    struct Grp { uint32_t g, x, hi; int k; int32_t id[U]; };
+    auto fetch = [&](Grp &n) {
         uint32_t g = 0;
         if (lane == 0) g = atomicAdd(&tl->next_group, 1u);
-        return __shfl_sync(0xffffffffu, g, 0);
-    };
-    int k = 0;
-    for (uint32_t g = grab(); g < n_groups;) {
-        const uint32_t g_next = grab();
-        while (g >= gtab[k + 1]) { ++k; CPM_CHECK(k < nz, "g %u k %d nz %d n_groups %u", g, k, nz, n_groups); }
-        const int z = z0 + k;
-        CPM_CHECK(z < NB, "z %d", z);
-        const uint32_t lo = max(ld_prev(a.start + z), slab_lo), hi = min(ld_prev(a.start + z + 1), slab_hi);
-        const uint32_t x = lo + (g - gtab[k]) * GS + lane;
-        int32_t id[U];
-        bool act[U];
+        n.g = __shfl_sync(0xffffffffu, g, 0);
+        if (n.g < n_groups) {
+            while (n.g >= gtab[k + 1]) { ++k; CPM_CHECK(k < nz, "g %u k %d nz %d n_groups %u", n.g, k, nz, n_groups); }
+            n.k = k;
+            n.hi = slab_lo + zlo[k + 1];
+            n.x = slab_lo + zlo[k] + (n.g - gtab[k]) * GS + lane;
+            CPM_CHECK(n.hi <= slab_hi && slab_lo + zlo[k] < n.hi, "lo %u hi %u slab %u %u k %d g %u", slab_lo + zlo[k], n.hi, slab_lo, slab_hi, k, n.g);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            act[u] = x + 32 * u < hi;
-            CPM_CHECK(hi <= slab_hi && lo >= slab_lo && lo < hi, "lo %u hi %u slab %u %u z %d k %d g %u", lo, hi, slab_lo, slab_hi, z, k, g);
-            id[u] = act[u] ? ld_prev(a.perm_cur + x + 32 * u) : 0;
+            for (int u = 0; u < U; ++u) n.id[u] = (n.x + 32 * u < n.hi) ? ld_prev(a.perm_cur + n.x + 32 * u) : 0;
         }
+    };
+    Grp cur, nxt;
+    fetch(cur);
+    while (cur.g < n_groups) {
+        fetch(nxt);
+        const int kz = cur.k, z = z0 + kz;
+        const uint32_t x = cur.x, hi = cur.hi;
         const bool is_zone = z < Ni;
         const double pd = is_zone ? __ldg(pd_t + z) : -1.0;
         const bool rowzero = is_zone ? (rz_t[z] != 0) : true;
-        const int slot = k & rmask;
-        const uint32_t use = (uint32_t)(k >> rshift);
+        const int slot = kz & rmask;
+        const uint32_t use = (uint32_t)(kz >> rshift);
         // ---- phase 1: Bernoulli drive decision (src/resampling.jl:11-22) ----
         double u2[U];
         uint32_t cell[U], m_stay[U];
-        bool srch[U], stay[U];
+        bool act[U], srch[U], stay[U];
         unsigned nd = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             bool drive = false;
+            act[u] = x + 32 * u < hi;
             u2[u] = 0.0; cell[u] = 0u;
             if (act[u] && is_zone) {
                 if (INJ) {
-                    drive = a.rng.u_drive[id[u] + uoff] <= pd;                  // :15 (<=; NaN p_drive parks)
-                    if (drive && !rowzero) u2[u] = a.rng.u_dest[id[u] + uoff];
+                    drive = a.rng.u_drive[cur.id[u] + uoff] <= pd;              // :15 (<=; NaN p_drive parks)
+                    if (drive && !rowzero) u2[u] = a.rng.u_dest[cur.id[u] + uoff];
                 } else {
                     uint32_t o[4];
-                    philox_words(a.rng, id[u], (uint32_t)a.step, 0u, o);
+                    philox_words(a.rng, cur.id[u], (uint32_t)a.step, 0u, o);
                     drive = u52(o[0], o[1]) <= pd;
                     u2[u] = u52(o[2], o[3]);
                     cell[u] = o[3] >> a.gshift;   // floor(u2 * G): the top log2(G) bits of the 52-bit uniform
@@ -308,49 +349,34 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
                     shi[u] = (open && !right) ? mid : shi[u];
                 }
             }
-            int dbin[U];
-            bool far[U];   // a trip to another zone: travel time from the truncated normal
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                dbin[u] = Ni; far[u] = false;
+                bool far = false;   // a trip to another zone: travel time from the truncated normal
+                int dbin = Ni;
                 if (srch[u]) {
                     const bool hit = slo[u] < Ni && u2[u] <= row[slo[u]];
-                    dbin[u] = hit ? slo[u] : Ni;
-                    CPM_CHECK(dbin[u] >= 0 && dbin[u] <= Ni, "dbin %d slo %d shi %d", dbin[u], slo[u], shi[u]);
-                    const uint32_t rank = atomicAdd(&hist[dbin[u]], 1u);
-                    a.dr[x + 32 * u] = (uint32_t)dbin[u] | (rank << 16);
-                    far[u] = hit && dbin[u] != z;
-                    if (TIME && dbin[u] == z) t_hi += 300ull;                           // :58-59
+                    dbin = hit ? slo[u] : Ni;
+                    CPM_CHECK(dbin >= 0 && dbin <= Ni, "dbin %d slo %d shi %d", dbin, slo[u], shi[u]);
+                    const uint32_t rank = atomicAdd(&hist[dbin], 1u);
+                    a.dr[x + 32 * u] = (uint32_t)dbin | (rank << 16);
+                    far = hit && dbin != z;
+                    if (TIME && dbin == z) t_hi += 300ull;                              // :58-59
+                }
+                if (TIME) {   // phase 3 (time only: counts mode), src/resampling.jl:53-70: queue the car, draw in dense batches
+                    const uint32_t m_far = __ballot_sync(0xffffffffu, far);
+                    if (far) {
+                        FarCar e; e.id = cur.id[u]; e.od = (uint32_t)z | ((uint32_t)dbin << 16);
+                        farq[(q_head + q_cnt + __popc(m_far & lt_mask)) & (kFarQueue - 1)] = e;
+                    }
+                    q_cnt += __popc(m_far);
                 }
             }
-            // ---- phase 3 (time only: counts mode), src/resampling.jl:53-70 ----
             if (TIME) {
-                double mean[U], sd[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    mean[u] = sd[u] = 0.0;
-                    if (far[u]) {
-                        const int64_t od = (int64_t)z + N * (int64_t)dbin[u];
-                        if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * a.hour); mean[u] = ms.x; sd[u] = ms.y; }
-                        else if (a.gather_policy) {
-                            mean[u] = ldg_stream(a.dm + od + NN * a.hour, l2_stream);
-                            sd[u] = ldg_stream(a.dm + od + NN * (a.hour + a.T_tab), l2_stream);
-                        } else {   // default policy: the 32-byte sector also holds the entries of the three neighbouring origins
-                            mean[u] = __ldg(a.dm + od + NN * a.hour);
-                            sd[u] = __ldg(a.dm + od + NN * (a.hour + a.T_tab));
-                        }
-                    }
+                __syncwarp();
+                while (q_cnt >= 32) {
+                    far_batch<INJ>(a, farq, q_head, 32, lane, uoff, l2_stream, t_hi, t_lo);
+                    q_head += 32; q_cnt -= 32;
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (far[u]) {
-                        double u3;
-                        if (INJ) u3 = a.rng.u_time[id[u] + uoff];
-                        else { uint32_t o[4]; philox_words(a.rng, id[u], (uint32_t)a.step, 1u, o); u3 = u52(o[0], o[1]); }
-                        double s = sd[u];
-                        if (s == 0.0) s = 0.1 * mean[u];
-                        fx_add(t_hi, t_lo, truncnormal(mean[u], s, u3));
-                    }
             }
         }
         // this group is done with the row; the warp that finishes the bin's last group re-arms the slot
@@ -360,13 +386,17 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
             // earlier bin (rare) and has to wait for its own use before it reports in
             while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }
             __threadfence_block();
-            if (atomicAdd(&tl->zdone[slot], 1u) + 1u == gtab[k + 1] - gtab[k]) {
+            if (atomicAdd(&tl->zdone[slot], 1u) + 1u == gtab[kz + 1] - gtab[kz]) {
                 mbar_wait(&tl->full[slot], use & 1u);   // nobody may have waited for this bin's row: it must have landed before the
                 tl->zdone[slot] = 0u;                   // buffer and its barrier are armed again
-                arm(slot, k + R);
+                arm(slot, kz + R);
             }
         }
-        g = g_next;
+        cur = nxt;
+    }
+    if (TIME) {   // the rest of the queue
+        __syncwarp();
+        far_batch<INJ>(a, farq, q_head, q_cnt, lane, uoff, l2_stream, t_hi, t_lo);
     }
     __syncthreads();
 
@@ -383,18 +413,25 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
     }
 #endif
     // One global atomic per destination this CTA saw: the return value is where this CTA's cars start inside the
-    // destination's bucket.  The counters are one per 256 bytes (one L2 slice each: profiles/r2 micro-benchmark C).
+    // destination's bucket.  The counters are one per 256 bytes (one L2 slice each: profiles/r2 micro-benchmark C); every
+    // CTA starts at a different bin, so that the CTAs (which finish together) do not queue up on the same counters.
     {
         uint2 *__restrict__ Mrow = a.M + (size_t)blockIdx.x * NB;
         constexpr int B = 4;
+        const int rot = (int)(((uint64_t)blockIdx.x * (uint64_t)NB) / gridDim.x);
         for (int b0 = tid; b0 < NB; b0 += B * THREADS) {
             uint32_t h[B], gb[B];
+            int bb[B];
 #pragma unroll
-            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; h[q] = b < NB ? hist[b] : 0u; }
+            for (int q = 0; q < B; ++q) {
+                const int b = b0 + q * THREADS;
+                bb[q] = b + rot < NB ? b + rot : b + rot - NB;
+                h[q] = b < NB ? hist[bb[q]] : 0u;
+            }
 #pragma unroll
-            for (int q = 0; q < B; ++q) gb[q] = h[q] ? atomicAdd(a.tot + (size_t)(b0 + q * THREADS) * kTotStride, h[q]) : 0u;
+            for (int q = 0; q < B; ++q) gb[q] = h[q] ? atomicAdd(a.tot + (size_t)bb[q] * kTotStride, h[q]) : 0u;
 #pragma unroll
-            for (int q = 0; q < B; ++q) { const int b = b0 + q * THREADS; if (b < NB) Mrow[b] = make_uint2(h[q], gb[q]); }
+            for (int q = 0; q < B; ++q) if (b0 + q * THREADS < NB) Mrow[bb[q]] = make_uint2(h[q], gb[q]);
         }
     }
 
@@ -412,6 +449,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
             if (lo32) atomicAdd(a.t_lo, lo32);
         }
     }
+    (void)W;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -667,10 +705,13 @@ bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g)
     const int threads = env_int("CPM_BUCKET_THREADS", 1024) == 512 ? 512 : 1024;
     const int per_sm = 1024 / threads;
     const size_t cap = kSmemCap / per_sm - (per_sm > 1 ? 1024 : 0);
-    const size_t fixed1 = hist_bytes(N) + gtab_bytes(N) + kSampleTail, row = (size_t)ldc * 8;
+    // hist | gtab | zlo | tail | one travel-time queue per warp (resampling steps; the IVP variant just leaves it unused)
+    const size_t fixed1 = hist_bytes(N) + gtab_bytes(N) + zlo_bytes(N) + kSampleTail + (size_t)(threads / 32) * kFarQueue * sizeof(FarCar),
+                 row = (size_t)ldc * 8;
     if (fixed1 + row > cap) return false;
+    // 4 row buffers by default: deeper rings starve L1 (measured at cfg2: 8 buffers 60 us per launch, 4 buffers 49 us)
     int ring = (int)std::min<size_t>(kMaxRing, (cap - fixed1) / row);
-    const int ring_env = env_int("CPM_BUCKET_RING", 0);
+    const int ring_env = env_int("CPM_BUCKET_RING", 4);
     if (ring_env >= 1 && ring_env < ring) ring = ring_env;
     while (ring & (ring - 1)) ring &= ring - 1;   // a power of two: slot and use of a bin are a mask and a shift
     const size_t fixed2 = scatter_smem(NB, 0) + 64;
@@ -718,12 +759,10 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int THREADS, int U>
+template <int THREADS, int U, bool TIME>
 static cudaError_t launch_sample_variant(const BucketArgs &a, const BucketGeom &g, cudaStream_t st)
 {
-    const bool inj = a.rng.mode == 1, time = a.with_time != 0;
-    void (*k)(const BucketArgs) = inj ? (time ? k_bucket_sample<THREADS, U, true, true> : k_bucket_sample<THREADS, U, true, false>)
-                                      : (time ? k_bucket_sample<THREADS, U, false, true> : k_bucket_sample<THREADS, U, false, false>);
+    void (*k)(const BucketArgs) = a.rng.mode == 1 ? k_bucket_sample<THREADS, U, true, TIME> : k_bucket_sample<THREADS, U, false, TIME>;
     cudaError_t e = ensure_smem(k, g.smem_sample);
     if (e != cudaSuccess) return e;
     return launch_pdl(k, (unsigned)g.n_slabs, THREADS, g.smem_sample, st, a);
@@ -731,10 +770,13 @@ static cudaError_t launch_sample_variant(const BucketArgs &a, const BucketGeom &
 
 int launch_bucket_sample(const BucketArgs &a, const BucketGeom &g, cudaStream_t st)
 {
-    static const int U = env_int("CPM_BUCKET_U", 2) == 1 ? 1 : 2;
+    // cars per lane and group: 4 in the IVP steps (four independent Philox / search chains per lane hide their latencies;
+    // 40 registers), 2 in the resampling steps (the travel-time code needs the registers)
+    static const int U_ivp = env_int("CPM_BUCKET_U", 4) == 2 ? 2 : 4;
     cudaError_t e;
-    if (g.threads == 512) e = (U == 1) ? launch_sample_variant<512, 1>(a, g, st) : launch_sample_variant<512, 2>(a, g, st);
-    else e = (U == 1) ? launch_sample_variant<1024, 1>(a, g, st) : launch_sample_variant<1024, 2>(a, g, st);
+    if (a.with_time) e = g.threads == 512 ? launch_sample_variant<512, 2, true>(a, g, st) : launch_sample_variant<1024, 2, true>(a, g, st);
+    else if (U_ivp == 2) e = g.threads == 512 ? launch_sample_variant<512, 2, false>(a, g, st) : launch_sample_variant<1024, 2, false>(a, g, st);
+    else e = g.threads == 512 ? launch_sample_variant<512, 4, false>(a, g, st) : launch_sample_variant<1024, 4, false>(a, g, st);
     return e == cudaSuccess ? 1 : -1;
 }
 
