@@ -369,6 +369,68 @@ def bench_cfg5(ctx, tm, rank, world, torch, dist_, N, cars_per_rank, n_steps, sp
             "lost_visits_rank0": int(lost)}
 
 
+def bench_mode_j(ctx, lib, _lib, tm, dm_F, dist_F, N, cpz, T, passes, pinned):
+    """Mode J = the strict drop-in: the seven reference functions in main.jl:82-98 order through the C ABI's host-pointer
+    entry points, Julia-layout trajectory arrays (state Int64[C,T], transition Float64[C,T,4]) crossing PCIe both ways.
+    SURVEY 8(d): 67.2 B per transition at cfg2 (16 B state + 32 B transition slots + table share).  `pinned`: the host
+    arrays are page-locked (the Julia shim registers the arrays it hands out) or ordinary pageable memory."""
+    import ctypes as C
+    C_ = N * cpz
+    CT = C_ * T
+
+    def buf(n, dtype):
+        if pinned:
+            raw, hnd = pinned_f64(lib, n * np.dtype(dtype).itemsize // 8 + 1)
+            handles.append(hnd)
+            return raw.view(dtype)[:n]
+        a_ = np.empty(n, dtype=dtype)
+        a_[:] = 0                                           # touch the pages once, like a Julia `zeros`
+        return a_
+
+    handles = []
+    state, trans = buf(CT, np.int64), buf(4 * CT, np.float64)
+    pdrive, pdest, init = buf(N * T, np.float64), buf(N * N * T, np.float64), buf(C_, np.int64)
+    parking, driving, traffic = buf(N * T, np.float64), buf(N * T, np.float64), buf(T, np.float64)
+    dm = dm_F if pinned else np.array(dm_F, order="F", copy=True)
+    dist = dist_F if pinned else np.array(dist_F, order="F", copy=True)
+    P = lambda a_: C.c_void_p(a_.ctypes.data)
+    rng = _lib.CRng()
+    rng.mode, rng.seed = _lib.RNG_PHILOX, 4321
+    A, lost = C.c_double(), C.c_int64()
+    h = ctx._h
+
+    def one_pass():
+        ck = _lib.check
+        ck(lib.cpm_create_pdrive(h, P(dm), P(dist), N, T, PARAMS["p_min"], PARAMS["p_max"], PARAMS["e_drive"], P(pdrive)))   # main.jl:82
+        ck(lib.cpm_create_pdestin(h, P(dm), N, T, float(PARAMS["e_dest"]), P(pdest)))                                       # :85
+        ck(lib.cpm_initialize_states(h, C_, T, cpz, P(state), P(trans)))                                                     # :88
+        rng.stream = 0
+        ck(lib.cpm_solve_ivp(h, P(state), P(trans), P(pdrive), P(pdest), C_, N, T, C.byref(rng), P(init), C.byref(lost)))    # :91
+        state[:C_] = init                                                                                                    # :92
+        rng.stream = 1
+        ck(lib.cpm_resampling(h, P(state), P(trans), C_, N, T, P(pdrive), P(pdest), P(dm), P(dist), C.byref(rng), C.byref(lost)))   # :95
+        ck(lib.cpm_average_driving_time(h, C_, T, 0.0, P(trans), C.byref(A)))                                                # :98
+        ck(lib.cpm_zone_histogram(h, P(state), P(trans), C_, N, T, P(parking), P(driving), P(traffic)))                      # saveresults.jl:6-28
+        return A.value
+
+    one_pass()                                              # warm-up: allocations, kernel loading
+    skipped0 = ctx.uploads_skipped
+    t0 = time.perf_counter()
+    ms, A_val = tm.run(lambda: [one_pass() for _ in range(passes)][-1])
+    wall = time.perf_counter() - t0
+    skipped = (ctx.uploads_skipped - skipped0) // passes
+    for hnd in handles:
+        lib.cpm_host_free(hnd)
+    trans_n = (2 * T - 1) * C_
+    peak, _ = measured_peak()
+    rate = trans_n * passes / (ms * 1e-3)
+    return {"value": rate, "unit": "transitions/s", "ms_per_pass": ms / passes, "wall_ms_per_pass": 1e3 * wall / passes, "passes": passes,
+            "host_memory": "page-locked" if pinned else "pageable", "uploads_skipped_per_pass": int(skipped),
+            "bytes_per_transition": 67.2, "roofline_frac": rate * 67.2 / 1e9 / peak, "A_drive": A_val,
+            "note": "createpdrive, createpdestin, initializestates, solveinitialvalueproblem, resampling, averagedrivingtime, zone histogram "
+                    "through the host-pointer entry points; the 2.3 GB trajectory arrays are returned to the host after initializestates, the IVP and the resampling day, as the Julia API requires"}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------------------
@@ -510,6 +572,13 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
                       "A_drive_rel_err": float(abs(A_gpu - res["A"]) / abs(res["A"])), "p_drive_max_rel_err": pd_err,
                       "what": "oracle (Philox) vs libcpm on the same cars of the bench city: IVP end state, per-zone parked / driving counts of the resampling day (exact), A_drive (1e-10), p_drive (1e-12)"}
             f2.close()
+        # ---- mode J: the seven reference functions with host arrays (the strict drop-in) ----
+        mode_j = None
+        if world == 1 and not args.no_mode_j:
+            fleet.close()
+            city.release_tables()
+            mode_j = {"page_locked": bench_mode_j(ctx, lib, _lib, tm, dm_F, dist_F, N, cpz, T, args.mode_j_passes, True),
+                      "pageable": bench_mode_j(ctx, lib, _lib, tm, dm_F, dist_F, N, cpz, T, 1, False)}
         lib.cpm_host_free(p1); lib.cpm_host_free(p2)
         city.close(); fleet.close()
 
@@ -562,6 +631,7 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             "result_check": {"A_drive": A_drive, "lost": int(lost), "parking_sum_t1": float(parking[:, 0].sum()),
                              "parity_vs_oracle": parity},
             "multi_gpu": multi,
+            "extra": {"mode_j": mode_j},
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
@@ -586,6 +656,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rows", action="store_true", help="skip the e2e_rows arm (density 0.09 city from CSV columns)")
     ap.add_argument("--no-multi", action="store_true", help="skip the multi_gpu block (cfg3 / cfg4 / cfg5)")
+    ap.add_argument("--no-mode-j", action="store_true", help="skip the mode-J block (the seven Julia-named functions with host arrays)")
+    ap.add_argument("--mode-j-passes", type=int, default=2)
     ap.add_argument("--cities", type=int, default=34, help="cfg3: cities of the batch")
     ap.add_argument("--sweep-sets", type=int, default=1024, help="cfg4: parameter sets (4096 = the whole grid)")
     ap.add_argument("--cfg5-zones", type=int, default=10000)

@@ -57,6 +57,8 @@ SIGNATURES = {
     "cpm_ctx_launch_count": (_i32, [_vp, C.POINTER(_i64)]),
     "cpm_ctx_profile_begin": (_i32, [_vp]),
     "cpm_ctx_profile_end": (_i32, [_vp, C.POINTER(_d), C.POINTER(_i64)]),
+    "cpm_ctx_set_input_cache": (_i32, [_vp, _i32]),
+    "cpm_ctx_uploads_skipped": (_i32, [_vp, C.POINTER(_i64)]),
     "cpm_host_alloc": (_i32, [_i64, _pp]),
     "cpm_host_free": (_i32, [_vp]),
     "cpm_host_register": (_i32, [_vp, _i64]),

@@ -123,6 +123,14 @@ struct cpm_ctx {
     // scratch objects of the host API (re-used across calls)
     cpm_city *h_city = nullptr;
     cpm_fleet *h_fleet = nullptr;
+    // Host-array cache of the host API: which caller array (pointer, size, sampled checksum) each resident device copy
+    // mirrors.  main.jl:82-98 passes the same datamatrix to createpdrive, createpdestin and resampling, the same p_dest to
+    // solveinitialvalueproblem and resampling, and the trajectory arrays from one call to the next: a match skips the upload.
+    struct HostKey { const void *p = nullptr; size_t n = 0; uint64_t sig = 0; bool valid = false; };
+    HostKey hk_mean, hk_sd, hk_dist, hk_pdest, hk_state, hk_trans[4];
+    bool cache_inputs = true;
+    int64_t uploads_skipped = 0;
+    struct SweepState *sweep = nullptr;      // fleets and staging kept between cpm_sweep calls
     DevBuf traj_state, traj_trans, u[4], tmp, partials, scalars;
     // optional timing of the sampling kernel: one event pair per day (consecutive launches of the step kernel)
     bool profiling = false;
@@ -217,11 +225,15 @@ extern "C" int32_t cpm_ctx_create(int32_t device, void *stream, cpm_ctx **out)
     return CPM_OK;
 }
 
+struct SweepState;
+static void sweep_state_free(SweepState *&w);
+
 extern "C" int32_t cpm_ctx_destroy(cpm_ctx *ctx)
 {
     if (!ctx) return CPM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
+    sweep_state_free(ctx->sweep);
     if (ctx->h_city) cpm_city_destroy(ctx->h_city);
     if (ctx->h_fleet) cpm_fleet_destroy(ctx->h_fleet);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
@@ -1124,6 +1136,30 @@ extern "C" int32_t cpm_sample_dataset_rows(cpm_city *city, cpm_fleet *fleet, con
     return rc;
 }
 
+static bool hk_match(cpm_ctx *ctx, const cpm_ctx::HostKey &k, const void *p, size_t n);
+static void hk_set(cpm_ctx::HostKey &k, const void *p, size_t n);
+
+// Sweep state that survives between cpm_sweep calls on a context: the grouped initial fleet, two work fleets and a
+// pinned staging block.  The notebook's searches issue one trial (or a small batch) per call
+// (README.md:1133-1316, :1461-1681): re-creating fleets and re-uploading the 19 MB initial state cost more than a trial.
+struct SweepState {
+    cpm_fleet *base = nullptr, *work[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    struct Stage { unsigned long long tc[64]; Scalars sc; } *stage = nullptr;   // pinned, [2]
+    cpm_ctx::HostKey init_key;
+    int64_t C = 0, N = 0;
+};
+static void sweep_state_free(SweepState *&w)
+{
+    if (!w) return;
+    if (w->base) cpm_fleet_destroy(w->base);
+    for (auto &f : w->work) if (f) cpm_fleet_destroy(f);
+    for (auto &e : w->done) if (e) cudaEventDestroy(e);
+    if (w->stage) cudaFreeHost(w->stage);
+    delete w;
+    w = nullptr;
+}
+
 extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const cpm_params *params, int64_t P,
                              uint64_t seed, const uint32_t *streams, int64_t *traffic_counts, double *A_drive,
                              double *parking)
@@ -1132,30 +1168,65 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
     cpm_ctx *ctx = city->ctx;
     TRY(use(ctx));
     const int64_t N = city->N, T = city->T;
-    cpm_fleet *base = nullptr, *work = nullptr;
-    int32_t rc = cpm_fleet_create(ctx, C, &base);
-    if (rc == CPM_OK) rc = cpm_fleet_create(ctx, C, &work);
-    if (rc == CPM_OK) rc = cpm_fleet_set_zones(base, initial_zones);
-    if (rc == CPM_OK && P >= 2) rc = cpm_city_prepare_multi_day(city);   // many days on the same inputs
-    // every set starts from the same state: group it by zone once, the per-set copy takes the grouping along
-    if (rc == CPM_OK && P >= 2 && city_alloc_cdf(city) == CPM_OK && city->G > 0 && bucket_supported(N, city->ldc)) rc = fleet_bucketize_async(base, N, city->ldc);
-    std::vector<unsigned long long> tc((size_t)T);
-    bool have_e_dest = false;
-    double cur_e_dest = 0.0;
+    ARG(T <= 64);
+    SweepState *&w = ctx->sweep;
+    if (w && (w->C != C || w->N != N)) sweep_state_free(w);
+    if (!w) {
+        w = new (std::nothrow) SweepState();
+        if (!w) return fail(CPM_ERR_OOM, "host allocation failed");
+        w->C = C; w->N = N;
+        int32_t rc = cpm_fleet_create(ctx, C, &w->base);
+        for (int k = 0; k < 2 && rc == CPM_OK; ++k) rc = cpm_fleet_create(ctx, C, &w->work[k]);
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&w->done[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&w->stage), 2 * sizeof(SweepState::Stage), cudaHostAllocDefault);
+        if (rc != CPM_OK || e != cudaSuccess) {
+            sweep_state_free(w);
+            return rc != CPM_OK ? rc : fail(CPM_ERR_CUDA, "sweep state: %s", cudaGetErrorString(e));
+        }
+    }
+    TRY(city_alloc_cdf(city));
+    const bool bucket = city->G > 0 && bucket_supported(N, city->ldc);
+    // the initial state: uploaded and grouped by zone once, as long as the caller passes the same unchanged array
+    const bool same_init = hk_match(ctx, w->init_key, initial_zones, (size_t)C * sizeof(int64_t)) && w->base->zone_valid &&
+                           (!bucket || (w->base->bucket_valid && w->base->bucket_N == N));
+    if (!same_init) {
+        TRY(cpm_fleet_set_zones(w->base, initial_zones));
+        if (bucket) TRY(fleet_bucketize_async(w->base, N, city->ldc));   // every set takes a copy of the grouping along
+        hk_set(w->init_key, initial_zones, (size_t)C * sizeof(int64_t));
+    }
+    if (P >= 2) TRY(cpm_city_prepare_multi_day(city));   // many days on the same inputs: (mean, std) pair table
     // sets are processed grouped by e_dest (stable), so every distinct e_dest builds its CDF once; results land at the
     // caller's index p and the Philox stream is tied to p, so the order of evaluation is invisible to the caller
     std::vector<int64_t> order((size_t)P);
     for (int64_t k = 0; k < P; ++k) order[(size_t)k] = k;
     std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return params[x].e_dest < params[y].e_dest; });
+    bool have_e_dest = false;
+    double cur_e_dest = 0.0;
+    int64_t in_flight[2] = {-1, -1};   // the set whose results sit in work[k] / stage[k]
+    auto collect = [&](int k) -> int32_t {   // results of the set that ran in slot k (its copies were enqueued behind it)
+        const int64_t p = in_flight[k];
+        if (p < 0) return CPM_OK;
+        CU(cudaEventSynchronize(w->done[k]));
+        if (traffic_counts) for (int64_t t = 0; t < T; ++t) traffic_counts[t + T * p] = (int64_t)w->stage[k].tc[t];
+        if (A_drive) A_drive[p] = w->stage[k].sc.time_sum / ((double)C * (double)T * 60 * 60);
+        in_flight[k] = -1;
+        return CPM_OK;
+    };
+    int32_t rc = CPM_OK;
     for (int64_t q = 0; rc == CPM_OK && q < P; ++q) {
         const int64_t p = order[(size_t)q];
         const cpm_params &pr = params[p];
+        const int k = (int)(q & 1);
+        rc = collect(k);   // slot k is free again; the other slot's set is still running: the host stays one set ahead
+        if (rc != CPM_OK) break;
+        cpm_fleet *work = w->work[k];
         if (!have_e_dest || pr.e_dest != cur_e_dest || !city->have_cdf) {   // CDFs are shared by sets with equal e_dest
             rc = city_build_pdestin_async(city, pr.e_dest, false);
             have_e_dest = true; cur_e_dest = pr.e_dest;
         }
         if (rc == CPM_OK) rc = city_build_pdrive_async(city, pr.p_min, pr.p_max, pr.e_drive);   // mean_sum cached
-        if (rc == CPM_OK) rc = cpm_fleet_copy_zones(work, base);                                  // README.md:1014,1549
+        if (rc == CPM_OK) rc = cpm_fleet_copy_zones(work, w->base);                                // README.md:1014,1549
         cpm_day_opts o;
         memset(&o, 0, sizeof o);
         o.n_steps = T; o.steps_per_hour = 1; o.with_time = 1; o.sampler = CPM_SAMPLER_AUTO;
@@ -1166,28 +1237,67 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
         if (rc != CPM_OK) break;
         const double *d_parking = work->norm_out.as<double>();
         const unsigned long long *d_tc = reinterpret_cast<const unsigned long long *>(d_parking + (size_t)N * T + T);
-        Scalars sc;
-        cudaError_t e = cudaMemcpyAsync(tc.data(), d_tc, (size_t)T * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&sc, work->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st);
+        cudaError_t e = cudaMemcpyAsync(w->stage[k].tc, d_tc, (size_t)T * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&w->stage[k].sc, work->scalars.p, sizeof(Scalars), cudaMemcpyDeviceToHost, ctx->st);
         if (e == cudaSuccess && parking)
             e = cudaMemcpyAsync(parking + (size_t)N * T * p, d_parking, (size_t)N * T * sizeof(double), cudaMemcpyDeviceToHost, ctx->st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+        if (e == cudaSuccess) e = cudaEventRecord(w->done[k], ctx->st);
         if (e != cudaSuccess) { rc = fail(CPM_ERR_CUDA, "sweep copy-out: %s", cudaGetErrorString(e)); break; }
-        if (traffic_counts) for (int64_t t = 0; t < T; ++t) traffic_counts[t + T * p] = (int64_t)tc[(size_t)t];
-        if (A_drive) A_drive[p] = sc.time_sum / ((double)C * (double)T * 60 * 60);
+        in_flight[k] = p;
     }
-    cpm_fleet_destroy(base);
-    cpm_fleet_destroy(work);
+    for (int k = 0; k < 2; ++k) { const int32_t r2 = collect(k); if (rc == CPM_OK) rc = r2; }
+    if (rc != CPM_OK) cudaStreamSynchronize(ctx->st);
     return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Host API: the reference's Julia functions with host pointers
 // ------------------------------------------------------------------------------------------------
+// Sampled 64-bit checksum of a host array: the first and last 128 words and 65,536 evenly spaced ones.  It decides
+// whether the device copy made from this array in an earlier call is still current.  Contract: the
+// reference never writes into datamatrix, distance_matrix_km, p_drive or p_dest after building them, and the trajectory
+// arrays change only through these functions and `state_matrix[:,1] = initial_state` (main.jl:92), which is always
+// re-read; a caller that edits arrays in place between calls switches the cache off (cpm_ctx_set_input_cache).
+static uint64_t host_sig(const void *p, size_t bytes)
+{
+    const uint64_t *w = static_cast<const uint64_t *>(p);
+    const size_t n = bytes / 8;
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)bytes;
+    auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29; };
+    if (n <= 65536 + 256) { for (size_t k = 0; k < n; ++k) mix(w[k]); return h; }
+    for (size_t k = 0; k < 128; ++k) { mix(w[k]); mix(w[n - 1 - k]); }
+    const size_t step = n / 65536;
+    for (size_t k = 0; k < 65536; ++k) mix(w[k * step + (k % step)]);
+    return h;
+}
+static bool hk_match(cpm_ctx *ctx, const cpm_ctx::HostKey &k, const void *p, size_t n)
+{
+    const bool hit = ctx->cache_inputs && k.valid && k.p == p && k.n == n && k.sig == host_sig(p, n);
+    if (hit) ++ctx->uploads_skipped;
+    return hit;
+}
+static void hk_set(cpm_ctx::HostKey &k, const void *p, size_t n) { k.p = p; k.n = n; k.sig = host_sig(p, n); k.valid = true; }
+static void hk_clear_city(cpm_ctx *ctx) { ctx->hk_mean.valid = ctx->hk_sd.valid = ctx->hk_dist.valid = ctx->hk_pdest.valid = false; }
+static void hk_clear_traj(cpm_ctx *ctx) { ctx->hk_state.valid = false; for (auto &k : ctx->hk_trans) k.valid = false; }
+
+extern "C" int32_t cpm_ctx_set_input_cache(cpm_ctx *ctx, int32_t enabled)
+{
+    ARG(ctx != nullptr);
+    ctx->cache_inputs = enabled != 0;
+    if (!enabled) { hk_clear_city(ctx); hk_clear_traj(ctx); }
+    return CPM_OK;
+}
+extern "C" int32_t cpm_ctx_uploads_skipped(cpm_ctx *ctx, int64_t *count)
+{
+    ARG(ctx && count);
+    *count = ctx->uploads_skipped;
+    return CPM_OK;
+}
+
 static int32_t host_city(cpm_ctx *ctx, int64_t N, int64_t T, cpm_city **out)
 {
-    if (ctx->h_city && (ctx->h_city->N != N || ctx->h_city->T != T)) { cpm_city_destroy(ctx->h_city); ctx->h_city = nullptr; }
-    if (!ctx->h_city) TRY(cpm_city_create(ctx, N, T, &ctx->h_city));
+    if (ctx->h_city && (ctx->h_city->N != N || ctx->h_city->T != T)) { cpm_city_destroy(ctx->h_city); ctx->h_city = nullptr; hk_clear_city(ctx); }
+    if (!ctx->h_city) { TRY(cpm_city_create(ctx, N, T, &ctx->h_city)); hk_clear_city(ctx); }
     *out = ctx->h_city;
     return CPM_OK;
 }
@@ -1199,6 +1309,34 @@ static int32_t host_fleet(cpm_ctx *ctx, int64_t C, cpm_fleet **out)
     return CPM_OK;
 }
 
+// Brings the parts of the caller's inputs a call needs into the host-API city (asynchronously on the context's stream;
+// the caller synchronises before it returns).  datamatrix = [mean slab | std slab].
+static int32_t host_inputs(cpm_ctx *ctx, cpm_city *c, const double *datamatrix, const double *distance_matrix_km, bool need_mean,
+                           bool need_sd, bool need_dist)
+{
+    TRY(city_alloc_inputs(c));
+    const size_t NN = (size_t)c->N * c->N, slab = NN * c->T * sizeof(double);
+    const char *dmb = reinterpret_cast<const char *>(datamatrix);
+    if (need_mean && !hk_match(ctx, ctx->hk_mean, dmb, slab)) {
+        CU(cudaMemcpyAsync(c->dm.p, dmb, slab, cudaMemcpyHostToDevice, ctx->st));
+        hk_set(ctx->hk_mean, dmb, slab);
+        ctx->hk_pdest.valid = false;   // tables derived from the old means are gone with them
+        city_invalidate(c);
+    }
+    if (need_sd && !hk_match(ctx, ctx->hk_sd, dmb + slab, slab)) {
+        CU(cudaMemcpyAsync(c->dm.as<char>() + slab, dmb + slab, slab, cudaMemcpyHostToDevice, ctx->st));
+        hk_set(ctx->hk_sd, dmb + slab, slab);
+        c->have_msd = false;
+    }
+    if (need_dist && !hk_match(ctx, ctx->hk_dist, distance_matrix_km, NN * sizeof(double))) {
+        CU(cudaMemcpyAsync(c->dist.p, distance_matrix_km, NN * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        hk_set(ctx->hk_dist, distance_matrix_km, NN * sizeof(double));
+        c->have_meansum = false;
+    }
+    c->have_inputs = ctx->hk_mean.valid && ctx->hk_sd.valid && ctx->hk_dist.valid;
+    return CPM_OK;
+}
+
 extern "C" int32_t cpm_create_pdrive(cpm_ctx *ctx, const double *datamatrix, const double *distance_matrix_km, int64_t N,
                                      int64_t T, double p_min, double p_max, double e_drive, double *p_drive_out)
 {
@@ -1206,9 +1344,14 @@ extern "C" int32_t cpm_create_pdrive(cpm_ctx *ctx, const double *datamatrix, con
     ARG(datamatrix && distance_matrix_km && p_drive_out && N >= 1 && T >= 1);
     cpm_city *c;
     TRY(host_city(ctx, N, T, &c));
-    TRY(cpm_city_upload(c, datamatrix, distance_matrix_km));
-    TRY(city_build_pdrive_async(c, p_min, p_max, e_drive));
-    return cpm_city_get_pdrive(c, p_drive_out);
+    // only the mean slab [N,N,T,1] and the distances are read (src/createpdrive.jl:16-18)
+    TRY(host_inputs(ctx, c, datamatrix, distance_matrix_km, true, false, true));
+    const bool full = c->have_inputs;
+    c->have_inputs = true;
+    int32_t rc = city_build_pdrive_async(c, p_min, p_max, e_drive);
+    if (rc == CPM_OK) rc = cpm_city_get_pdrive(c, p_drive_out);
+    c->have_inputs = full;
+    return rc;
 }
 
 extern "C" int32_t cpm_create_pdestin(cpm_ctx *ctx, const double *datamatrix, int64_t N, int64_t T, double e_dest,
@@ -1219,15 +1362,14 @@ extern "C" int32_t cpm_create_pdestin(cpm_ctx *ctx, const double *datamatrix, in
     cpm_city *c;
     TRY(host_city(ctx, N, T, &c));
     // only the mean slab [N,N,T,1] is read (src/createpdestin.jl:13,23)
-    TRY(city_alloc_inputs(c));
-    CU(cudaMemcpyAsync(c->dm.p, datamatrix, (size_t)N * N * T * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
-    const bool had_inputs = c->have_inputs;
+    TRY(host_inputs(ctx, c, datamatrix, nullptr, true, false, false));
+    const bool full = c->have_inputs;
     c->have_inputs = true;
-    city_invalidate(c);
     int32_t rc = city_build_pdestin_async(c, e_dest);
     if (rc == CPM_OK) rc = cpm_city_get_pdest(c, p_dest_out);
-    c->have_inputs = false;   // std slab and distances were not uploaded: do not let later calls trust them
-    (void)had_inputs;
+    c->have_inputs = full;
+    // the device keeps p_dest and its sampling CDF: a later call that passes this very array back finds them resident
+    if (rc == CPM_OK) hk_set(ctx->hk_pdest, p_dest_out, (size_t)N * N * T * sizeof(double));
     return rc;
 }
 
@@ -1242,6 +1384,8 @@ extern "C" int32_t cpm_initialize_states(cpm_ctx *ctx, int64_t C, int64_t T, int
     CU(cudaMemcpyAsync(state, ctx->traj_state.p, CT * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaMemcpyAsync(trans, ctx->traj_trans.p, CT * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    hk_set(ctx->hk_state, state, CT * sizeof(int64_t));
+    for (int k = 0; k < 4; ++k) hk_set(ctx->hk_trans[k], trans + (size_t)k * CT, CT * sizeof(double));
     return CPM_OK;
 }
 
@@ -1273,11 +1417,19 @@ static int32_t host_sample(cpm_ctx *ctx, int64_t *state, double *trans, const do
     TRY(host_fleet(ctx, C, &fleet));
     if (!ivp) {
         ARG(datamatrix && distance_matrix_km);
-        TRY(cpm_city_upload(city, datamatrix, distance_matrix_km));
+        TRY(host_inputs(ctx, city, datamatrix, distance_matrix_km, true, true, true));
     }
     TRY(cpm_city_set_pdrive(city, p_drive));
-    TRY(cpm_city_set_pdest(city, p_dest));
+    const size_t pd_bytes = (size_t)N * N * T * sizeof(double);
+    if (!(city->have_cdf && hk_match(ctx, ctx->hk_pdest, p_dest, pd_bytes))) {   // else: p_dest and its CDF are resident
+        TRY(cpm_city_set_pdest(city, p_dest));
+        hk_set(ctx->hk_pdest, p_dest, pd_bytes);
+    }
     const size_t CT = (size_t)C * T;
+    const bool fresh = ctx->traj_state.cap < CT * sizeof(int64_t) || ctx->traj_trans.cap < CT * 4 * sizeof(double);
+    if (fresh) hk_clear_traj(ctx);
+    bool pre[2] = { false, false };   // did the device copies of slots 1-2 mirror the caller's array when this call began?
+    if (ivp) for (int k = 0; k < 2; ++k) { pre[k] = hk_match(ctx, ctx->hk_trans[k], trans + (size_t)k * CT, CT * sizeof(double)); if (pre[k]) --ctx->uploads_skipped; }
     TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
     TRY(ctx->traj_trans.ensure(CT * 4 * sizeof(double)));
     int64_t *d_state = ctx->traj_state.as<int64_t>();
@@ -1285,9 +1437,12 @@ static int32_t host_sample(cpm_ctx *ctx, int64_t *state, double *trans, const do
     // column 1 of state_matrix is the only state input (src/resampling.jl:12 at t = 1)
     CU(cudaMemcpyAsync(d_state, state, (size_t)C * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
     LAUNCH(ctx, launch_i64_to_i32(d_state, fleet->zone.as<int32_t>(), C, ctx->st));
+    fleet->zone_valid = true; fleet->bucket_valid = false;
     const int64_t n_steps = ivp ? T - 1 : T;
     if (!ivp)   // slots 3-4 of non-driving cars keep their previous contents (src/resampling.jl:55-77)
-        CU(cudaMemcpyAsync(d_trans + 2 * CT, trans + 2 * CT, 2 * CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+        for (int k = 2; k < 4; ++k)
+            if (!hk_match(ctx, ctx->hk_trans[k], trans + (size_t)k * CT, CT * sizeof(double)))
+                CU(cudaMemcpyAsync(d_trans + (size_t)k * CT, trans + (size_t)k * CT, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
     if (n_steps >= 1) {
         cpm_day_opts o;
         memset(&o, 0, sizeof o);
@@ -1308,6 +1463,16 @@ static int32_t host_sample(cpm_ctx *ctx, int64_t *state, double *trans, const do
     CU(cudaMemcpyAsync(&sc, fleet->scalars.p, sizeof sc, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     if (n_lost_out) *n_lost_out = n_steps >= 1 ? (int64_t)sc.lost : 0;
+    // Host and device trajectories agree from here on wherever this call wrote or read them.  An IVP call leaves column T of
+    // slots 1-2 and all of slots 3-4 alone on both sides: those keys stay what they were (slots 1-2 only if the host
+    // array still matched before the call).
+    if (ctx->cache_inputs) {
+        hk_set(ctx->hk_state, state, CT * sizeof(int64_t));
+        for (int k = 0; k < 4; ++k) {
+            if (!ivp) hk_set(ctx->hk_trans[k], trans + (size_t)k * CT, CT * sizeof(double));
+            else if (k < 2) { if (pre[k]) hk_set(ctx->hk_trans[k], trans + (size_t)k * CT, CT * sizeof(double)); else ctx->hk_trans[k].valid = false; }
+        }
+    } else hk_clear_traj(ctx);
     return CPM_OK;
 }
 
@@ -1334,12 +1499,18 @@ extern "C" int32_t cpm_average_driving_time(cpm_ctx *ctx, int64_t C, int64_t T, 
     TRY(use(ctx));
     ARG(trans && A_drive_out && C >= 1 && T >= 1);
     const size_t CT = (size_t)C * T;
-    TRY(ctx->tmp.ensure(CT * sizeof(double)));
     const int np = sampler_grid((int64_t)CT);
     TRY(ctx->partials.ensure((size_t)np * sizeof(double)));
     TRY(ctx->scalars.ensure(sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->tmp.p, trans + 2 * CT, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 3
-    LAUNCH(ctx, launch_sum_f64(ctx->tmp.as<double>(), (int64_t)CT, ctx->partials.as<double>(), np, ctx->scalars.as<double>(), ctx->st));
+    const double *d_slot3;
+    if (ctx->traj_trans.cap >= 4 * CT * sizeof(double) && hk_match(ctx, ctx->hk_trans[2], trans + 2 * CT, CT * sizeof(double)))
+        d_slot3 = ctx->traj_trans.as<double>() + 2 * CT;   // the trajectory resampling() just returned is still resident
+    else {
+        TRY(ctx->tmp.ensure(CT * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->tmp.p, trans + 2 * CT, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 3
+        d_slot3 = ctx->tmp.as<double>();
+    }
+    LAUNCH(ctx, launch_sum_f64(d_slot3, (int64_t)CT, ctx->partials.as<double>(), np, ctx->scalars.as<double>(), ctx->st));
     double s = 0.0;
     CU(cudaMemcpyAsync(&s, ctx->scalars.p, sizeof s, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1402,15 +1573,24 @@ extern "C" int32_t cpm_zone_histogram(cpm_ctx *ctx, const int64_t *state, const 
     TRY(use(ctx));
     ARG(state && trans && C >= 1 && N >= 1 && T >= 1);
     const size_t CT = (size_t)C * T, NT = (size_t)N * T;
-    TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
-    TRY(ctx->tmp.ensure(CT * sizeof(double)));
     TRY(ctx->partials.ensure(2 * NT * sizeof(uint32_t) + (2 * NT + 2 * T) * sizeof(double)));
     uint32_t *cnt = ctx->partials.as<uint32_t>();
     double *outp = reinterpret_cast<double *>(cnt + 2 * NT);   // NT even multiples keep 8-byte alignment
-    CU(cudaMemcpyAsync(ctx->traj_state.p, state, CT * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemcpyAsync(ctx->tmp.p, trans, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 1: drive flag
+    const int64_t *d_state;
+    const double *d_flag;
+    const bool resident = ctx->traj_state.cap >= CT * sizeof(int64_t) && ctx->traj_trans.cap >= 4 * CT * sizeof(double) &&
+                          hk_match(ctx, ctx->hk_state, state, CT * sizeof(int64_t)) && hk_match(ctx, ctx->hk_trans[0], trans, CT * sizeof(double));
+    if (resident) { d_state = ctx->traj_state.as<int64_t>(); d_flag = ctx->traj_trans.as<double>(); }
+    else {
+        hk_clear_traj(ctx);   // the trajectory buffers are about to be overwritten with this call's arrays
+        TRY(ctx->traj_state.ensure(CT * sizeof(int64_t)));
+        TRY(ctx->tmp.ensure(CT * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->traj_state.p, state, CT * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(ctx->tmp.p, trans, CT * sizeof(double), cudaMemcpyHostToDevice, ctx->st));   // slot 1: drive flag
+        d_state = ctx->traj_state.as<int64_t>(); d_flag = ctx->tmp.as<double>();
+    }
     CU(cudaMemsetAsync(cnt, 0, 2 * NT * sizeof(uint32_t), ctx->st));
-    LAUNCH(ctx, launch_traj_histogram(ctx->traj_state.as<int64_t>(), ctx->tmp.as<double>(), C, N, T, cnt, cnt + NT, ctx->st));
+    LAUNCH(ctx, launch_traj_histogram(d_state, d_flag, C, N, T, cnt, cnt + NT, ctx->st));
     LAUNCH(ctx, launch_normalise_counts(cnt, cnt + NT, N, T, C, outp, outp + NT, outp + 2 * NT,
                                         reinterpret_cast<unsigned long long *>(outp + 2 * NT + T), ctx->st));
     if (parking) CU(cudaMemcpyAsync(parking, outp, NT * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));

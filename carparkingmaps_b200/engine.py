@@ -78,6 +78,16 @@ class Context:
         L.check(L.lib().cpm_ctx_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def set_input_cache(self, enabled: bool):
+        """Host API only: reuse device copies of unchanged host arrays across calls (default on)."""
+        L.check(L.lib().cpm_ctx_set_input_cache(self._h, int(bool(enabled))))
+
+    @property
+    def uploads_skipped(self) -> int:
+        n = C.c_int64()
+        L.check(L.lib().cpm_ctx_uploads_skipped(self._h, C.byref(n)))
+        return n.value
+
     def profile_begin(self):
         L.check(L.lib().cpm_ctx_profile_begin(self._h))
 

@@ -82,6 +82,12 @@ int32_t cpm_ctx_launch_count(cpm_ctx *ctx, int64_t *count);
  * end() synchronises and returns the summed device time and the number of launches it covers. */
 int32_t cpm_ctx_profile_begin(cpm_ctx *ctx);
 int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int64_t *step_launches);
+/* Host-array cache of the host API (default on): the device copies of datamatrix, distance_matrix_km, p_dest and the
+ * trajectory arrays are keyed by (host pointer, size, sampled 64-bit checksum); when a later call of the main.jl:82-98
+ * sequence passes the same unchanged array, its upload (and, for p_dest, the CDF build) is skipped.  Switch it off for
+ * callers that edit those arrays in place between calls.  cpm_ctx_uploads_skipped counts the hits. */
+int32_t cpm_ctx_set_input_cache(cpm_ctx *ctx, int32_t enabled);
+int32_t cpm_ctx_uploads_skipped(cpm_ctx *ctx, int64_t *count);
 /* pinned host memory for callers that want full-rate PCIe copies */
 int32_t cpm_host_alloc(int64_t bytes, void **out);
 int32_t cpm_host_free(void *p);
