@@ -193,6 +193,7 @@ static int32_t use(cpm_ctx *ctx)
 // ------------------------------------------------------------------------------------------------
 extern "C" int32_t cpm_version(void) { return CPM_VERSION; }
 extern "C" const char *cpm_last_error(void) { return g_err.c_str(); }
+extern "C" void cpm_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }   // for multi.cu; not part of cpm.h
 
 extern "C" int32_t cpm_device_count(int32_t *count)
 {

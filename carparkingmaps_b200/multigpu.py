@@ -166,3 +166,58 @@ def run_sweep(city, initial_zones, params, *, seed=0, rank=0, world=1, want_park
         if want_parking:
             pk[:, :, idx] = r[2]
     return tc, A, pk
+
+
+# ------------------------------------------------------------------------------------------------
+# several GPUs from ONE process, through the C ABI (what a single-process Julia host calls): csrc/multi.cu
+# ------------------------------------------------------------------------------------------------
+def device_count() -> int:
+    import ctypes as C
+    from . import _lib as L
+    n = C.c_int32()
+    L.check(L.lib().cpm_device_count(C.byref(n)))
+    return n.value
+
+
+def sample_datasets_multi(devices, datasets, *, cars_per_zone=1000, T=24, params=None, seed=0):
+    """main.jl's city / dataset loop over `devices` in one C call (cpm_sample_datasets_multi): `datasets` is a list of
+    (datamatrix[N,N,T,2], distance_matrix_km[N,N]) host arrays.  Returns [(parking[N,T], traffic[T], A_drive, n_lost)]."""
+    import ctypes as C
+    from . import _lib as L
+    from .engine import _f64F
+    params = params or dict(e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9)
+    pr = L.CParams(float(params["e_drive"]), float(params["e_dest"]), float(params["p_min"]), float(params["p_max"]))
+    n = len(datasets)
+    dms = [_f64F(d[0]) for d in datasets]
+    dists = [_f64F(d[1]) for d in datasets]
+    Ns = np.array([d.shape[0] for d in dists], dtype=np.int64)
+    parking = [np.empty((int(N), T), order="F") for N in Ns]
+    traffic = [np.empty(T) for _ in Ns]
+    A, lost = np.empty(n), np.empty(n, dtype=np.int64)
+    ptrs = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    L.check(L.lib().cpm_sample_datasets_multi(dev.ctypes.data, len(dev), n, Ns.ctypes.data, T, ptrs(dms), ptrs(dists), C.byref(pr),
+                                              int(cars_per_zone), int(seed), ptrs(parking), ptrs(traffic), A.ctypes.data, lost.ctypes.data))
+    return [(parking[k], traffic[k], float(A[k]), int(lost[k])) for k in range(n)]
+
+
+def split_city_multi(devices, datamatrix, distance_matrix_km, *, cars_per_zone, n_steps, steps_per_hour=1, with_time=True,
+                     params=None, seed=0, stream=1):
+    """One city, cars split over `devices`, one NCCL all-reduce of the counts (cpm_split_city_multi).
+    Returns (parking int64[N,n_steps], driving int64[N,n_steps], time_sum, n_lost, allreduce_ms)."""
+    import ctypes as C
+    from . import _lib as L
+    from .engine import _f64F
+    params = params or dict(e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9)
+    pr = L.CParams(float(params["e_drive"]), float(params["e_dest"]), float(params["p_min"]), float(params["p_max"]))
+    dm, dist = _f64F(datamatrix), _f64F(distance_matrix_km)
+    N, T = dist.shape[0], dm.shape[2]
+    parking = np.empty((N, n_steps), dtype=np.int64, order="F")
+    driving = np.empty((N, n_steps), dtype=np.int64, order="F")
+    ts, ar = C.c_double(), C.c_double()
+    lost = C.c_int64()
+    dev = np.ascontiguousarray(devices, dtype=np.int32)
+    L.check(L.lib().cpm_split_city_multi(dev.ctypes.data, len(dev), N, T, dm.ctypes.data, dist.ctypes.data, C.byref(pr), int(cars_per_zone),
+                                         int(n_steps), int(steps_per_hour), int(with_time), int(seed), int(stream), parking.ctypes.data,
+                                         driving.ctypes.data, C.byref(ts), C.byref(lost), C.byref(ar)))
+    return parking, driving, ts.value, lost.value, ar.value

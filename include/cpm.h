@@ -267,6 +267,30 @@ int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const
                   int64_t P, uint64_t seed, const uint32_t *streams, int64_t *traffic_counts,
                   double *A_drive, double *parking);
 
+/* ---------------------------------------------------------------------------------------- */
+/* Several GPUs from one host process                                                       */
+/* ---------------------------------------------------------------------------------------- */
+/* The city loop / dataset loop of main.jl:46-103, :71-103 (serial in the reference) over n_devices GPUs in ONE call: one
+ * host thread and one context per device, datasets assigned by longest-processing-time on N*cars_per_zone*(2T-1) +
+ * 3*N*N*T, one dataset pass of main.jl:82-98 each (cpm_sample_dataset_host; dataset k uses seed + k), no collective on
+ * the data path.  HOST arrays: datamatrix[k] [N[k],N[k],T,2], distance_matrix_km[k] [N[k],N[k]]; outputs per dataset
+ * (any of the output arrays may be NULL): parking_out[k] [N[k],T], traffic_out[k] [T], A_drive_out[k], n_lost_out[k]. */
+int32_t cpm_sample_datasets_multi(const int32_t *devices, int32_t n_devices, int64_t n_datasets, const int64_t *N,
+                                  int64_t T, const double *const *datamatrix, const double *const *distance_matrix_km,
+                                  const cpm_params *params, int64_t cars_per_zone, uint64_t seed,
+                                  double *const *parking_out, double *const *traffic_out, double *A_drive_out,
+                                  int64_t *n_lost_out);
+/* ONE city whose cars are split over the devices (contiguous ranges, global Philox counters: the result does not depend
+ * on the number of devices), tables replicated, n_steps steps (table hour = step / steps_per_hour), then one NCCL
+ * all-reduce (SUM) of the uint32 count blocks; NCCL is loaded with dlopen("libnccl.so.2") on first use.
+ * Outputs (host): parking / driving Int64 [N,n_steps] of the whole fleet, driving-time sum (s), lost-car visits,
+ * device time of the all-reduce alone (ms; 0 with one device).  Any output pointer may be NULL. */
+int32_t cpm_split_city_multi(const int32_t *devices, int32_t n_devices, int64_t N, int64_t T, const double *datamatrix,
+                             const double *distance_matrix_km, const cpm_params *params, int64_t cars_per_zone,
+                             int64_t n_steps, int64_t steps_per_hour, int32_t with_time, uint64_t seed, uint32_t stream,
+                             int64_t *parking_out, int64_t *driving_out, double *time_sum_out, int64_t *n_lost_out,
+                             double *allreduce_ms_out);
+
 #ifdef __cplusplus
 }
 #endif
