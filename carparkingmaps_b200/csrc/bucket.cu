@@ -153,7 +153,7 @@ __device__ __forceinline__ void far_batch(const BucketArgs &a, const FarCar *q, 
 }
 
 template <int THREADS, int U, bool INJ, bool TIME>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const BucketArgs a)
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sample(const BucketArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GS = 32 * U, W = THREADS / 32;
@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_sample(const
 #pragma unroll
         for (int u = 0; u < U; ++u) any_srch |= srch[u];
         if (__any_sync(0xffffffffu, any_srch)) {
-            while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }   // the slot still serves an earlier bin (rare)
+            if (lane == 0) while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }   // the slot still serves an earlier bin (rare)
+            __syncwarp();
             mbar_wait(&tl->full[slot], use & 1u);   // every lane observes the completion of the row copy
             const double *row = ring + (size_t)slot * a.ldc;
             const uint16_t *gd = reinterpret_cast<const uint16_t *>(row + a.goff);
@@ -509,7 +510,7 @@ __device__ __forceinline__ int bin_of_slot(const uint32_t *start, int nb, uint32
 // k_bucket_scatter: cars move to their destination bucket (state update, src/resampling.jl:81-83).
 // ------------------------------------------------------------------------------------------------
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_bucket_scatter(const ScatterArgs a)
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_scatter(const ScatterArgs a)
 {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     const int NB = a.NB, NBp = (NB + 3) & ~3;
@@ -698,15 +699,19 @@ static size_t scatter_smem(int NB, int64_t slab)
 
 // Slabs (= CTAs of both kernels), slab size, CTA width and ring depth.  One fat CTA per SM: a slab as large as the
 // 16-bit rank and the scatter kernel's shared-memory sort allow, more slabs (whole waves) only beyond that.
-bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g)
+bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, int with_time, BucketGeom *g)
 {
     if (N + 1 > 65535 || C < 1 || C > 0x7fffffff) return false;
     const int NB = (int)N + 1;
-    const int threads = env_int("CPM_BUCKET_THREADS", 1024) == 512 ? 512 : 1024;
-    const int per_sm = 1024 / threads;
+    // CTA shape: 1,024 threads, one CTA per SM.  The IVP kernel (40-46 registers) may also run as two CTAs of 768 or 512
+    // threads per SM (CPM_BUCKET_IVP_THREADS); the resampling kernel needs 58 registers and stays at 1,024 x 1.
+    int threads = with_time ? env_int("CPM_BUCKET_THREADS", 1024) : env_int("CPM_BUCKET_IVP_THREADS", env_int("CPM_BUCKET_THREADS", 1024));
+    if (threads != 512 && threads != 768) threads = 1024;
+    if (with_time && threads == 768) threads = 1024;
+    const int per_sm = threads == 1024 ? 1 : 2;
     const size_t cap = kSmemCap / per_sm - (per_sm > 1 ? 1024 : 0);
-    // hist | gtab | zlo | tail | one travel-time queue per warp (resampling steps; the IVP variant just leaves it unused)
-    const size_t fixed1 = hist_bytes(N) + gtab_bytes(N) + zlo_bytes(N) + kSampleTail + (size_t)(threads / 32) * kFarQueue * sizeof(FarCar),
+    // hist | gtab | zlo | tail | one travel-time queue per warp (resampling steps only)
+    const size_t fixed1 = hist_bytes(N) + gtab_bytes(N) + zlo_bytes(N) + kSampleTail + (with_time ? (size_t)(threads / 32) * kFarQueue * sizeof(FarCar) : 0),
                  row = (size_t)ldc * 8;
     if (fixed1 + row > cap) return false;
     // 4 row buffers by default: deeper rings starve L1 (measured at cfg2: 8 buffers 60 us per launch, 4 buffers 49 us)
@@ -725,6 +730,7 @@ bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g)
     g->n_slabs = (int)n;
     g->slab = (C + n - 1) / n;
     g->threads = threads;
+    g->threads_scatter = per_sm == 1 ? 1024 : 512;
     g->ring = ring;
     g->smem_sample = fixed1 + (size_t)ring * row;
     g->smem_scatter = scatter_smem(NB, g->slab);
@@ -734,7 +740,7 @@ bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g)
 bool bucket_supported(int64_t N, int64_t ldc)
 {
     BucketGeom g;
-    return bucket_geometry(N, ldc, 1, &g);
+    return bucket_geometry(N, ldc, 1, 1, &g) && bucket_geometry(N, ldc, 1, 0, &g);
 }
 
 // opt in to > 48 KB of dynamic shared memory.  The attribute belongs to the CURRENT device's copy of the kernel, so it
@@ -770,20 +776,21 @@ static cudaError_t launch_sample_variant(const BucketArgs &a, const BucketGeom &
 
 int launch_bucket_sample(const BucketArgs &a, const BucketGeom &g, cudaStream_t st)
 {
-    // cars per lane and group: 4 in the IVP steps (four independent Philox / search chains per lane hide their latencies;
-    // 40 registers), 2 in the resampling steps (the travel-time code needs the registers)
+    // cars per lane and group: 4 in the IVP steps by default (four independent Philox / search chains per lane), 2 in the
+    // resampling steps (the travel-time code needs the registers) and in the two-CTAs-per-SM IVP shapes
     static const int U_ivp = env_int("CPM_BUCKET_U", 4) == 2 ? 2 : 4;
     cudaError_t e;
     if (a.with_time) e = g.threads == 512 ? launch_sample_variant<512, 2, true>(a, g, st) : launch_sample_variant<1024, 2, true>(a, g, st);
-    else if (U_ivp == 2) e = g.threads == 512 ? launch_sample_variant<512, 2, false>(a, g, st) : launch_sample_variant<1024, 2, false>(a, g, st);
-    else e = g.threads == 512 ? launch_sample_variant<512, 4, false>(a, g, st) : launch_sample_variant<1024, 4, false>(a, g, st);
+    else if (g.threads == 768) e = launch_sample_variant<768, 2, false>(a, g, st);
+    else if (g.threads == 512) e = launch_sample_variant<512, 2, false>(a, g, st);
+    else e = U_ivp == 2 ? launch_sample_variant<1024, 2, false>(a, g, st) : launch_sample_variant<1024, 4, false>(a, g, st);
     return e == cudaSuccess ? 1 : -1;
 }
 
 int launch_bucket_scatter(const ScatterArgs &a, const BucketGeom &g, cudaStream_t st)
 {
     cudaError_t e;
-    if (g.threads == 512) {
+    if (g.threads_scatter == 512) {
         e = ensure_smem(k_bucket_scatter<512>, g.smem_scatter);
         if (e == cudaSuccess) e = launch_pdl(k_bucket_scatter<512>, (unsigned)g.n_slabs, 512, g.smem_scatter, st, a);
     } else {

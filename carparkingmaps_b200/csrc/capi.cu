@@ -765,14 +765,14 @@ static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, c
 // bucket sampler: cars grouped by zone, CDF rows staged in shared memory (bucket.cu)
 // Group the cars of a fleet by zone from its car-id indexed zone array: perm[0] (car ids by bin), the bucket starts, the
 // bucket sizes (cnt_cur) and the first bin of every slab.  Leaves the fleet in the state a finished bucket day leaves it in.
-static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N, int64_t ldc, cudaStream_t st = nullptr)
+static int32_t fleet_bucketize_async(cpm_fleet *f, int64_t N, int64_t ldc, int with_time, cudaStream_t st = nullptr)
 {
     cpm_ctx *ctx = f->ctx;
     if (!st) st = ctx->st;
     const int NB = (int)N + 1;
     if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
     BucketGeom g;
-    if (!bucket_geometry(N, ldc, f->C, &g)) return fail(CPM_ERR_ARG, "the bucket sampler does not support this city size");
+    if (!bucket_geometry(N, ldc, f->C, with_time, &g)) return fail(CPM_ERR_ARG, "the bucket sampler does not support this city size");
     TRY(f->perm[0].ensure((size_t)f->C * 4));
     TRY(f->cnt_cur.ensure((size_t)NB * 4)); TRY(f->start_tmp.ensure((size_t)(NB + 1) * 4)); TRY(f->cursor_tmp.ensure((size_t)NB * 4));
     TRY(f->first_zone.ensure((size_t)g.n_slabs * 4));
@@ -792,7 +792,7 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     const int NB = (int)N + 1;
     const int64_t S = o->n_steps;
     BucketGeom g;
-    if (!bucket_geometry(N, city->ldc, C, &g)) return fail(CPM_ERR_ARG, "the bucket sampler does not support this city size");
+    if (!bucket_geometry(N, city->ldc, C, o->with_time, &g)) return fail(CPM_ERR_ARG, "the bucket sampler does not support this city size");
     const size_t tot_words = (size_t)NB * kTotStride;
     TRY(f->perm[0].ensure((size_t)C * 4)); TRY(f->perm[1].ensure((size_t)C * 4));
     TRY(f->dest.ensure((size_t)C * 4));                                   // (destination, rank) per slot
@@ -806,7 +806,7 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     CU(cudaMemsetAsync(bdrv, 0, (size_t)S * NB * 4, ctx->st));
     CU(cudaMemsetAsync(tot, 0, 2 * tot_words * 4, ctx->st));
     const bool grouped = f->bucket_valid && f->bucket_N == N && f->geom.n_slabs == g.n_slabs && f->geom.slab == g.slab;
-    if (!grouped) TRY(fleet_bucketize_async(f, N, city->ldc));
+    if (!grouped) TRY(fleet_bucketize_async(f, N, city->ldc, o->with_time));
     // grouped (from the previous day, a copy of a grouped fleet, or just now): bucket sizes and bucket starts are current
     CU(cudaMemcpyAsync(bcnt, f->cnt_cur.p, (size_t)NB * 4, cudaMemcpyDeviceToDevice, ctx->st));
     Scalars *sc = f->scalars.as<Scalars>();
@@ -974,7 +974,7 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     // initializestates (main.jl:88) and the grouping of the cars by zone do not depend on the tables: second stream as well
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->aux_st));
     fleet->car_offset = 0; fleet->zone_valid = true; fleet->bucket_valid = false;
-    if (sampler != CPM_SAMPLER_GATHER && city->G > 0 && bucket_supported(N, city->ldc)) TRY(fleet_bucketize_async(fleet, N, city->ldc, ctx->aux_st));
+    if (sampler != CPM_SAMPLER_GATHER && city->G > 0 && bucket_supported(N, city->ldc)) TRY(fleet_bucketize_async(fleet, N, city->ldc, T > 1 ? 0 : 1, ctx->aux_st));
     CU(cudaEventRecord(ctx->ev_aux[1], ctx->aux_st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev_aux[1], 0));
     cpm_day_opts o;
@@ -1193,7 +1193,7 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
                            (!bucket || (w->base->bucket_valid && w->base->bucket_N == N));
     if (!same_init) {
         TRY(cpm_fleet_set_zones(w->base, initial_zones));
-        if (bucket) TRY(fleet_bucketize_async(w->base, N, city->ldc));   // every set takes a copy of the grouping along
+        if (bucket) TRY(fleet_bucketize_async(w->base, N, city->ldc, 1));   // every set takes a copy of the grouping along
         hk_set(w->init_key, initial_zones, (size_t)C * sizeof(int64_t));
     }
     if (P >= 2) TRY(cpm_city_prepare_multi_day(city));   // many days on the same inputs: (mean, std) pair table

@@ -67,7 +67,8 @@ constexpr int kTotStride = 64;   // uint32 words between two per-destination arr
 struct BucketGeom {
     int n_slabs;               // CTAs of k_bucket_sample / k_bucket_scatter (whole waves of one fat CTA per SM)
     int64_t slab;              // slots per CTA (<= 65,472: ranks are 16-bit)
-    int threads;               // CTA width of both kernels
+    int threads;               // CTA width of k_bucket_sample
+    int threads_scatter;       // CTA width of k_bucket_scatter
     int ring;                  // CDF row buffers per CTA
     size_t smem_sample, smem_scatter;
 };
@@ -99,7 +100,7 @@ struct ScatterArgs {
     int32_t *zone_out;         // nullable: car-id indexed zone (written on the last step of a day)
 };
 bool bucket_supported(int64_t N, int64_t ldc);
-bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, BucketGeom *g);
+bool bucket_geometry(int64_t N, int64_t ldc, int64_t C, int with_time, BucketGeom *g);
 int launch_bucket_sample(const BucketArgs &a, const BucketGeom &g, cudaStream_t st);
 int launch_bucket_scatter(const ScatterArgs &a, const BucketGeom &g, cudaStream_t st);
 int launch_bucketize(const int32_t *zone, int64_t C, int NB, uint32_t *cnt0, uint32_t *start, uint32_t *cursor_tmp,

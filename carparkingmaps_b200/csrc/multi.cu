@@ -73,7 +73,7 @@ struct Nccl {
     }
 };
 Nccl g_nccl;
-constexpr int kNcclUint32 = 3, kNcclUint64 = 5, kNcclSum = 0;   // ncclUint32, ncclUint64, ncclSum (nccl.h)
+constexpr int kNcclUint32 = 3, kNcclSum = 0;   // ncclUint32, ncclSum (nccl.h)
 
 }  // namespace
 
