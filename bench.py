@@ -345,11 +345,15 @@ def bench_cfg5(ctx, tm, rank, world, torch, dist_, N, cars_per_rank, n_steps, sp
     t_tab_ms, _ = tm.run(lambda: city.build_pdrive(0.1, 0.9, 0.5).build_pdestin(2, keep_p_dest=False))
     fleet = Fleet(ctx, C_rank).init(cpz, car_offset=off)
     rng = lambda stream: Rng(mode="philox", seed=7, stream=stream, car_offset=off)
-    fleet.run_day(city, min(n_steps, 2), with_time=True, steps_per_hour=sph, rng=rng(0))      # warm-up
+    # warm-up with the shape of the timed run: buffers of a day's size are allocated and touched once, kernels loaded
+    fleet.run_day(city, n_steps, with_time=True, steps_per_hour=sph, rng=rng(0))
     fleet.init(cpz, car_offset=off)
     ms, _ = tm.run(lambda: fleet.run_day(city, n_steps, with_time=True, steps_per_hour=sph, rng=rng(1)))
     counts = fleet_counts_tensor(fleet)
     local_total = int(counts[: N].sum().item())                # cars this rank holds at step 0
+    warm = torch.zeros_like(counts)
+    allreduce_counts(warm)                                    # NCCL sets up its channels for this message size on first use
+    del warm
     ar_ms, _ = tm.run(lambda: allreduce_counts(counts))
     full_day = torch.zeros(2 * N * 1440, dtype=torch.int32, device="cuda")   # the count block of the whole 1,440-step day
     allreduce_counts(full_day)

@@ -152,6 +152,13 @@ __device__ __forceinline__ void far_batch(const BucketArgs &a, const FarCar *q, 
     }
 }
 
+// wait until ring slot's generation word shows `use`; bounded like mbar_wait(): a logic error must trap, not hang the GPU
+__device__ __forceinline__ void spin_until_gen(const uint32_t *gen, uint32_t use)
+{
+    for (uint32_t spin = 0; *reinterpret_cast<const volatile uint32_t *>(gen) != use; ++spin)
+        if (spin > (1u << 26)) __trap();
+}
+
 template <int THREADS, int U, bool INJ, bool TIME>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sample(const BucketArgs a)
 {
@@ -264,6 +271,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
         const uint32_t x = cur.x, hi = cur.hi;
         const bool is_zone = z < Ni;
         const double pd = is_zone ? __ldg(pd_t + z) : -1.0;
+        // u <= p_drive on the 52-bit integer m of the uniform u = m * 2^-52:  m <= floor(p_drive * 2^52)  (exact: the scaling is a
+        // power of two and m is an integer); p_drive >= 1 lets every car drive, a negative or NaN p_drive none (:15)
+        const long long pd_m = pd >= 1.0 ? (1ll << 52) : (pd >= 0.0 ? __double2ll_rd(pd * 4503599627370496.0) : -1ll);
         const bool rowzero = is_zone ? (rz_t[z] != 0) : true;
         const int slot = kz & rmask;
         const uint32_t use = (uint32_t)(kz >> rshift);
@@ -284,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
                 } else {
                     uint32_t o[4];
                     philox_words(a.rng, cur.id[u], (uint32_t)a.step, 0u, o);
-                    drive = u52(o[0], o[1]) <= pd;
+                    drive = (long long)(((unsigned long long)o[1] << 20) | (unsigned long long)(o[0] >> 12)) <= pd_m;
                     u2[u] = u52(o[2], o[3]);
                     cell[u] = o[3] >> a.gshift;   // floor(u2 * G): the top log2(G) bits of the 52-bit uniform
                 }
@@ -318,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
 #pragma unroll
         for (int u = 0; u < U; ++u) any_srch |= srch[u];
         if (__any_sync(0xffffffffu, any_srch)) {
-            if (lane == 0) while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }   // the slot still serves an earlier bin (rare)
+            if (lane == 0) spin_until_gen(&tl->gen[slot], use);   // the slot still serves an earlier bin (rare)
             __syncwarp();
             mbar_wait(&tl->full[slot], use & 1u);   // every lane observes the completion of the row copy
             const double *row = ring + (size_t)slot * a.ldc;
@@ -336,19 +346,27 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
                     }
                 }
             }
-            for (;;) {
-                bool any = false;
+            // branch-free bisection step; a finished search re-reads row[slo] (slo <= N lies inside the row block)
+            auto bisect = [&]() {
 #pragma unroll
-                for (int u = 0; u < U; ++u) any |= slo[u] < shi[u];
-                if (!any) break;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {   // branch-free: a finished search re-reads row[slo] (slo <= N lies inside the row block)
+                for (int u = 0; u < U; ++u) {
                     const bool open = slo[u] < shi[u];
                     const int mid = (slo[u] + shi[u]) >> 1;
                     const bool right = row[mid] < u2[u];                                 // NaN compares false -> goes left
                     slo[u] = (open && right) ? mid + 1 : slo[u];
                     shi[u] = (open && !right) ? mid : shi[u];
                 }
+            };
+            // a warp needs ~4 steps anyway (its widest guide cell; a lane 2.7): four steps without loop control settle every
+            // cell of up to 15 entries, the loop behind them is for the rare wider one
+#pragma unroll
+            for (int it = 0; it < 4; ++it) bisect();
+            for (;;) {
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < U; ++u) any |= slo[u] < shi[u];
+                if (!__any_sync(0xffffffffu, any)) break;
+                bisect();
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -385,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
         if (lane == 0) {
             // zdone[slot] counts one use at a time: a group that never searched may get here while the slot still serves an
             // earlier bin (rare) and has to wait for its own use before it reports in
-            while (*reinterpret_cast<volatile uint32_t *>(&tl->gen[slot]) != use) { }
+            spin_until_gen(&tl->gen[slot], use);
             __threadfence_block();
             if (atomicAdd(&tl->zdone[slot], 1u) + 1u == gtab[kz + 1] - gtab[kz]) {
                 mbar_wait(&tl->full[slot], use & 1u);   // nobody may have waited for this bin's row: it must have landed before the
@@ -594,12 +612,20 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sca
     __syncthreads();
     // pass 2: consecutive threads hold consecutive cars of one destination -> the stores go out in runs
     const int n = hi - lo;
-    for (int p = tid; p < n; p += THREADS) {
-        const uint32_t d = sdst[p];
-        const int32_t car = sid[p];
-        CPM_CHECK(off[d] + (uint32_t)p < (uint32_t)a.C, "p %d d %u pos %u", p, d, off[d] + (uint32_t)p);
-        a.perm_next[off[d] + (uint32_t)p] = car;
-        if (a.zone_out) a.zone_out[car] = (d < (uint32_t)(NB - 1)) ? (int32_t)d + 1 : 0;   // last step: car-id indexed state
+    for (int p0 = tid; p0 < n; p0 += 4 * THREADS) {   // four independent load -> load -> store chains per trip
+        uint32_t d[4], pos[4];
+        int32_t car[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int p = p0 + q * THREADS; d[q] = p < n ? sdst[p] : 0u; car[q] = p < n ? sid[p] : 0; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pos[q] = off[d[q]] + (uint32_t)(p0 + q * THREADS);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (p0 + q * THREADS < n) {
+                CPM_CHECK(pos[q] < (uint32_t)a.C, "p %d d %u pos %u", p0 + q * THREADS, d[q], pos[q]);
+                a.perm_next[pos[q]] = car[q];
+                if (a.zone_out) a.zone_out[car[q]] = (d[q] < (uint32_t)(NB - 1)) ? (int32_t)d[q] + 1 : 0;   // last step: car-id indexed state
+            }
     }
 }
 
