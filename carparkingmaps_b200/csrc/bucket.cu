@@ -28,6 +28,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "kernels.h"
 #include "async.cuh"
@@ -769,15 +772,27 @@ bool bucket_supported(int64_t N, int64_t ldc)
     return bucket_geometry(N, ldc, 1, 1, &g) && bucket_geometry(N, ldc, 1, 0, &g);
 }
 
-// opt in to > 48 KB of dynamic shared memory.  The attribute belongs to the CURRENT device's copy of the kernel, so it
-// is set on every launch (a cheap host-side call) instead of being cached in a process-wide flag: contexts on
-// several devices and host threads share this library.
-template <typename K>
-static cudaError_t ensure_smem(K kernel, size_t bytes)
+// opt in to > 48 KB of dynamic shared memory.  The attribute belongs to the CURRENT device's copy of the kernel, and
+// contexts on several devices and host threads share this library: what has been granted is remembered per (device,
+// kernel) under a mutex, so that the steady state costs a table lookup instead of a driver call per launch (small
+// cities are bound by the host's launch rate).
+static cudaError_t ensure_smem_impl(const void *kernel, size_t bytes)
 {
     if (bytes <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &g = granted[std::make_pair(dev, kernel)];
+    if (bytes <= g) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) g = bytes;
+    return e;
 }
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t bytes) { return ensure_smem_impl(reinterpret_cast<const void *>(kernel), bytes); }
 
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args)

@@ -466,19 +466,41 @@ static int32_t city_build_pdrive_async(cpm_city *c, double p_min, double p_max, 
     c->have_pdrive = true;
     return CPM_OK;
 }
-static int32_t city_alloc_cdf(cpm_city *c)
+// layout of a CDF row block for N zones: N running sums, padding to goff doubles, then the guide table (G+1 uint16)
+static void cdf_layout(int64_t N, int32_t *goff, int32_t *G, int64_t *ldc)
 {
-    c->goff = (int32_t)((c->N + 1) / 2 * 2);                      // 16-byte aligned guide
-    c->G = 0;
-    if (c->N + 1 <= 65535) {                                       // guide entries are uint16
+    *goff = (int32_t)((N + 1) / 2 * 2);                           // 16-byte aligned guide
+    *G = 0;
+    if (N + 1 <= 65535) {                                          // guide entries are uint16
         int64_t g = 64;
         // 4-8 CDF entries per guide cell.  Measured at cfg2 (profiles/README.md): G = 512 beats 1,024 (fewer 2-byte guide
         // stores in the CDF build, 1 KB less per staged row) and 256 / 128 / 64 (more probes per search)
-        while (g < (c->N + 7) / 8 && g < 8192) g *= 2;
-        c->G = (int32_t)g;
+        while (g < (N + 7) / 8 && g < 8192) g *= 2;
+        *G = (int32_t)g;
     }
-    const int64_t guide_doubles = c->G ? ((int64_t)c->G + 1 + 7) / 8 * 2 : 0;   // (G+1) uint16 rounded up to 16 bytes
-    c->ldc = c->goff + guide_doubles;
+    const int64_t guide_doubles = *G ? ((int64_t)*G + 1 + 7) / 8 * 2 : 0;   // (G+1) uint16 rounded up to 16 bytes
+    *ldc = *goff + guide_doubles;
+}
+
+// Diagnostics (host arithmetic only, no device needed): the launch geometry the bucket sampler would use for N zones and C
+// cars.  out8 = {supported, n_slabs, slab, threads, ring, smem_sample, smem_scatter, ldc}.  Used by the CPU tests.
+extern "C" int32_t cpm_debug_bucket_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out8)
+{
+    ARG(out8 && N >= 1 && C >= 1);
+    int32_t goff, G;
+    int64_t ldc;
+    cdf_layout(N, &goff, &G, &ldc);
+    BucketGeom g;
+    memset(&g, 0, sizeof g);
+    const bool ok = G > 0 && bucket_supported(N, ldc) && bucket_geometry(N, ldc, C, with_time, &g);
+    const int64_t v[8] = { ok ? 1 : 0, g.n_slabs, g.slab, g.threads, g.ring, (int64_t)g.smem_sample, (int64_t)g.smem_scatter, ldc };
+    for (int k = 0; k < 8; ++k) out8[k] = v[k];
+    return CPM_OK;
+}
+
+static int32_t city_alloc_cdf(cpm_city *c)
+{
+    cdf_layout(c->N, &c->goff, &c->G, &c->ldc);
     TRY(c->cdf.ensure((size_t)c->N * c->ldc * c->T * sizeof(double)));
     TRY(c->rowzero.ensure((size_t)c->N * c->T));
     return CPM_OK;

@@ -267,6 +267,11 @@ int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const
                   int64_t P, uint64_t seed, const uint32_t *streams, int64_t *traffic_counts,
                   double *A_drive, double *parking);
 
+/* Diagnostics, host arithmetic only (no device needed): the launch geometry of the bucket sampler for N zones and C cars.
+ * out8 = {supported, slabs (CTAs), slots per slab, threads per CTA, CDF row buffers, bytes of shared memory of the
+ * sampling kernel, of the scatter kernel, doubles per CDF row block}. */
+int32_t cpm_debug_bucket_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out8);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Several GPUs from one host process                                                       */
 /* ---------------------------------------------------------------------------------------- */

@@ -1,0 +1,63 @@
+"""Launch geometry of the bucket sampler (csrc/bucket.cu bucket_geometry) as pure host arithmetic: every (zones, cars)
+pair must give slabs that cover the fleet, ranks that fit 16 bits, shared memory within the 227 KB of an sm_100a CTA and a
+power-of-two ring of CDF row buffers.  Runs without a GPU through cpm_debug_bucket_geometry."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from carparkingmaps_b200 import _lib as L
+
+SMEM_CAP = 227 * 1024
+
+
+def geom(N, cars, with_time):
+    out = (C.c_int64 * 8)()
+    L.check(L.lib().cpm_debug_bucket_geometry(int(N), int(cars), int(with_time), out))
+    keys = ("supported", "n_slabs", "slab", "threads", "ring", "smem_sample", "smem_scatter", "ldc")
+    return dict(zip(keys, list(out)))
+
+
+def check(N, cars, with_time):
+    g = geom(N, cars, with_time)
+    if not g["supported"]:
+        assert N > 10800, (N, cars, g)            # only rows too large for shared memory fall back to the gather sampler
+        return g
+    assert g["n_slabs"] >= 1 and g["n_slabs"] * g["slab"] >= cars
+    assert (g["n_slabs"] - 1) * g["slab"] < cars or g["n_slabs"] % 148 == 0      # no wave of empty slabs beyond a partial one
+    assert g["slab"] <= 65472                     # ranks inside a slab are 16-bit
+    assert g["threads"] in (512, 768, 1024)
+    assert g["ring"] in (1, 2, 4, 8)
+    per_sm = 1 if g["threads"] == 1024 else 2
+    assert g["smem_sample"] * per_sm <= SMEM_CAP and g["smem_scatter"] * per_sm <= SMEM_CAP
+    assert g["smem_sample"] >= g["ring"] * g["ldc"] * 8 + (N + 1) * 4
+    assert g["smem_scatter"] >= g["slab"] * 6 + (N + 1) * 8
+    return g
+
+
+@pytest.mark.parametrize("N,cpz", [(100, 1000), (2400, 1000), (500, 1000), (4000, 1000), (10000, 1250), (6, 1), (1, 7), (2400, 8)])
+def test_named_configs(N, cpz):
+    for wt in (0, 1):
+        g = check(N, N * cpz, wt)
+        assert g["supported"]
+    if (N, cpz) == (2400, 1000):
+        g = geom(N, N * cpz, 1)
+        assert g["n_slabs"] == 148 and g["threads"] == 1024 and g["ring"] == 4      # one fat CTA per SM, 4 row buffers
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(1, 14000), st.integers(1, 3000), st.booleans())
+def test_any_city_size(N, cpz, with_time):
+    check(N, N * cpz, with_time)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(1, 5000), st.integers(1, 2**31 - 1), st.booleans())
+def test_any_fleet_size(N, cars, with_time):
+    check(N, cars, with_time)
+
+
+def test_too_many_zones_fall_back():
+    assert not geom(30000, 30000 * 10, 1)["supported"]
+    assert not geom(70000, 70000, 0)["supported"]
