@@ -126,7 +126,7 @@ static_assert(sizeof(SampleTail) <= kSampleTail, "tail too small");
 
 // one entry of a warp's travel-time queue: a car that drives to another zone (src/resampling.jl:61-70)
 struct FarCar { int32_t id; uint32_t od; };   // od = origin | destination << 16
-constexpr int kFarQueue = 128;                 // entries per warp (a power of two, >= 32 * U + 31)
+constexpr int kFarQueue = 64;                  // entries per warp (a power of two, >= 63: a batch is drawn as soon as 32 cars wait)
 
 // travel-time draws of up to 32 queued cars, one per lane: (mean, std) gathered from datamatrix, second Philox call,
 // inverse-CDF truncated normal, fixed-point sum.  Dense lanes whatever the share of drivers in the groups was.
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int GS = 32 * U, W = THREADS / 32;
-    static_assert(!TIME || GS + 31 <= kFarQueue, "travel-time queue too small for this group size");
+    static_assert(kFarQueue >= 64, "travel-time queue: up to 31 waiting cars + 32 new ones");
     const int64_t N = a.N;
     const int Ni = (int)N, NB = Ni + 1;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -391,13 +391,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_bucket_sam
                         farq[(q_head + q_cnt + __popc(m_far & lt_mask)) & (kFarQueue - 1)] = e;
                     }
                     q_cnt += __popc(m_far);
-                }
-            }
-            if (TIME) {
-                __syncwarp();
-                while (q_cnt >= 32) {
-                    far_batch<INJ>(a, farq, q_head, 32, lane, uoff, l2_stream, t_hi, t_lo);
-                    q_head += 32; q_cnt -= 32;
+                    if (q_cnt >= 32) {   // a full batch: draw now (the queue never holds more than 63 cars)
+                        __syncwarp();
+                        far_batch<INJ>(a, farq, q_head, 32, lane, uoff, l2_stream, t_hi, t_lo);
+                        q_head += 32; q_cnt -= 32;
+                        __syncwarp();
+                    }
                 }
             }
         }
@@ -821,7 +820,9 @@ int launch_bucket_sample(const BucketArgs &a, const BucketGeom &g, cudaStream_t 
     // resampling steps (the travel-time code needs the registers) and in the two-CTAs-per-SM IVP shapes
     static const int U_ivp = env_int("CPM_BUCKET_U", 4) == 2 ? 2 : 4;
     cudaError_t e;
-    if (a.with_time) e = g.threads == 512 ? launch_sample_variant<512, 2, true>(a, g, st) : launch_sample_variant<1024, 2, true>(a, g, st);
+    static const int U_time = env_int("CPM_BUCKET_U_TIME", 2) == 4 ? 4 : 2;
+    if (a.with_time) e = g.threads == 512 ? launch_sample_variant<512, 2, true>(a, g, st)
+                       : (U_time == 4 ? launch_sample_variant<1024, 4, true>(a, g, st) : launch_sample_variant<1024, 2, true>(a, g, st));
     else if (g.threads == 768) e = launch_sample_variant<768, 2, false>(a, g, st);
     else if (g.threads == 512) e = launch_sample_variant<512, 2, false>(a, g, st);
     else e = U_ivp == 2 ? launch_sample_variant<1024, 2, false>(a, g, st) : launch_sample_variant<1024, 4, false>(a, g, st);
