@@ -41,3 +41,18 @@ def test_split_city_over_devices_equals_unsplit_run(ctx, N, cpz, sph):
     assert ts == ts0 and lost == lost0            # fixed-point time sum: bit-identical for any split
     assert ar_ms >= 0.0 and (len(devices) > 1) == (ar_ms > 0.0)
     city.close(); f.close()
+
+
+def test_large_rows_on_every_device(ctx):
+    """CDF rows of 2,000 zones need the > 48 KB shared-memory opt-in, which belongs to each device's copy of the kernels
+    (a process-wide flag skipped it on the second device): two such datasets, one per device."""
+    devices = list(range(min(2, device_count())))
+    Tn, N, cpz = 2, 2000, 6
+    data = [synth_city(N, Tn, seed=40 + k, density=0.5) for k in range(2)]
+    got = sample_datasets_multi(devices, data, cars_per_zone=cpz, T=Tn, seed=3)
+    for k, (dm, dist) in enumerate(data):
+        city, fleet = City(ctx, N, Tn).upload(dm, dist), Fleet(ctx, N * cpz)
+        want = sample_dataset(city, fleet, cars_per_zone=cpz, seed=3 + k)
+        np.testing.assert_array_equal(got[k][0], want[0])
+        assert got[k][2] == want[2] and got[k][3] == want[3]
+        city.close(); fleet.close()
