@@ -373,6 +373,38 @@ def bench_cfg5(ctx, tm, rank, world, torch, dist_, N, cars_per_rank, n_steps, sp
             "lost_visits_rank0": int(lost)}
 
 
+def bench_small_city(ctx, tm, T, passes=40, sets=64):
+    """BASELINE configs[0] (the reference's own CPU-runnable case: 100 zones x 1,000 cars): a pass is ~110 launches of
+    kernels that take a few microseconds each, so the host's launch rate bounds it.  Timed with direct launches and with
+    the pass replayed as a CUDA graph (cpm.h: cpm_ctx_set_graphs); results compared bit for bit.  Same for a 64-set sweep."""
+    from carparkingmaps_b200 import City, Fleet, sample_dataset, sweep
+    N, cpz, _ = WORKLOADS["cfg1"]
+    city = City(ctx, N, T).synth(seed=5, density=1.0)
+    fleet = Fleet(ctx, N * cpz)
+    init = np.repeat(np.arange(1, N + 1, dtype=np.int64), cpz)
+    grid = [(0.5 + 0.5 * (k % 4), 2.0, 0.05 + 0.002 * k, 0.95 - 0.003 * k) for k in range(sets)]
+    out = {"workload": f"cfg1: {N} zones x {cpz} cars, T={T}", "passes": passes, "sweep_sets": sets}
+    res = {}
+    for name, on in (("direct", False), ("graph", True)):
+        ctx.set_graphs(on)
+        for k in range(3):
+            sample_dataset(city, fleet, cars_per_zone=cpz, seed=k, **PARAMS)
+        l0, r0 = ctx.launches, ctx.graph_replays
+        ms, last = tm.run(lambda: [sample_dataset(city, fleet, cars_per_zone=cpz, seed=100 + k, **PARAMS) for k in range(passes)][-1])
+        sweep(city, init, grid[:4], seed=3)
+        ms_sw, sw = tm.run(lambda: sweep(city, init, grid, seed=3))
+        res[name] = (last, sw)
+        out[name] = {"ms_per_pass": ms / passes, "transitions_per_s": N * cpz * (2 * T - 1) * passes / (ms * 1e-3),
+                     "kernels_per_pass": (ctx.launches - l0) / passes, "graph_replays": ctx.graph_replays - r0,
+                     "sweep_ms_per_set": ms_sw / sets}
+    ctx.set_graphs(True)
+    (a, sa), (b, sb) = res["direct"], res["graph"]
+    out["identical"] = bool(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and
+                            np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1]))
+    city.close(); fleet.close()
+    return out
+
+
 def bench_mode_j(ctx, lib, _lib, tm, dm_F, dist_F, N, cpz, T, passes, pinned):
     """Mode J = the strict drop-in: the seven reference functions in main.jl:82-98 order through the C ABI's host-pointer
     entry points, Julia-layout trajectory arrays (state Int64[C,T], transition Float64[C,T,4]) crossing PCIe both ways.
@@ -481,6 +513,7 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
         ev1.record(stream)
         barrier()
         step_ms, step_launches = ctx.profile_end()
+        step_kernel = {1: "k_step_gather", 2: "k_bucket_sample", 3: "k_day_cars"}.get(fleet.last_sampler, "?")
         launches = ctx.launches - l0
         ms = ev0.elapsed_time(ev1)
         clk = clocks.finish()
@@ -585,6 +618,7 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
                       "pageable": bench_mode_j(ctx, lib, _lib, tm, dm_F, dist_F, N, cpz, T, 1, False)}
         lib.cpm_host_free(p1); lib.cpm_host_free(p2)
         city.close(); fleet.close()
+        small = bench_small_city(ctx, tm, T) if world == 1 and not args.no_small else None
 
         # ---- BASELINE's sharded configs, in the same run ----
         multi = None
@@ -626,7 +660,8 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             # dominant kernel: k_bucket_sample (one launch = one HMM step over all C cars).  Every third launch is bracketed
             # with CUDA events on the library's stream inside the timed region; `traffic` is the ncu dram__bytes_read+write
             # per launch of a committed capture of the SAME kernel source, or null (not a live figure).
-            "roofline": {"bound": "hbm", "kernel": "k_bucket_sample (per-step sampling kernel)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": step_kernel + (" (one launch runs all steps of a day; figures are per step)" if step_kernel == "k_day_cars" else " (per-step sampling kernel)"),
+                         "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": traffic_note,
                          "bytes_per_transition": B, "transitions_per_launch": C_, "avg_launch_ms": avg_launch_ms,
@@ -635,7 +670,7 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             "result_check": {"A_drive": A_drive, "lost": int(lost), "parking_sum_t1": float(parking[:, 0].sum()),
                              "parity_vs_oracle": parity},
             "multi_gpu": multi,
-            "extra": {"mode_j": mode_j},
+            "extra": {"mode_j": mode_j, "small_city": small},
         }
         if cpu_line is not None:
             line["cpu_baseline"] = cpu_line
@@ -661,6 +696,7 @@ def main():
     ap.add_argument("--no-rows", action="store_true", help="skip the e2e_rows arm (density 0.09 city from CSV columns)")
     ap.add_argument("--no-multi", action="store_true", help="skip the multi_gpu block (cfg3 / cfg4 / cfg5)")
     ap.add_argument("--no-mode-j", action="store_true", help="skip the mode-J block (the seven Julia-named functions with host arrays)")
+    ap.add_argument("--no-small", action="store_true", help="skip the small-city block (cfg1 with and without graph replay)")
     ap.add_argument("--mode-j-passes", type=int, default=2)
     ap.add_argument("--cities", type=int, default=34, help="cfg3: cities of the batch")
     ap.add_argument("--sweep-sets", type=int, default=1024, help="cfg4: parameter sets (4096 = the whole grid)")

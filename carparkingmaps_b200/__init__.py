@@ -6,8 +6,8 @@ synth.py (synthetic inputs), modelselection.py (the notebook's update rules on t
 julia/CarParkingMapsGPU.jl (the ccall shim a Julia host includes instead of src/*.jl).
 """
 from . import _lib
-from ._lib import CpmError, SAMPLER_AUTO, SAMPLER_BUCKET, SAMPLER_GATHER, build
+from ._lib import CpmError, SAMPLER_AUTO, SAMPLER_BUCKET, SAMPLER_CARS, SAMPLER_GATHER, build
 from .engine import City, Context, Fleet, Rng, sample_dataset, sample_dataset_host, sample_dataset_rows, sweep
 
 __all__ = ["City", "Context", "Fleet", "Rng", "sample_dataset", "sample_dataset_host", "sample_dataset_rows", "sweep", "build", "CpmError",
-           "SAMPLER_AUTO", "SAMPLER_GATHER", "SAMPLER_BUCKET"]
+           "SAMPLER_AUTO", "SAMPLER_GATHER", "SAMPLER_BUCKET", "SAMPLER_CARS"]

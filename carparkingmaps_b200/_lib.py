@@ -11,7 +11,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 CPM_OK = 0
 RNG_PHILOX, RNG_INJECTED = 0, 1
-SAMPLER_AUTO, SAMPLER_GATHER, SAMPLER_BUCKET = 0, 1, 2
+SAMPLER_AUTO, SAMPLER_GATHER, SAMPLER_BUCKET, SAMPLER_CARS = 0, 1, 2, 3
 
 
 class CpmError(RuntimeError):
@@ -59,6 +59,8 @@ SIGNATURES = {
     "cpm_ctx_profile_end": (_i32, [_vp, C.POINTER(_d), C.POINTER(_i64)]),
     "cpm_ctx_set_input_cache": (_i32, [_vp, _i32]),
     "cpm_ctx_uploads_skipped": (_i32, [_vp, C.POINTER(_i64)]),
+    "cpm_ctx_graph_replays": (_i32, [_vp, C.POINTER(_i64)]),
+    "cpm_ctx_set_graphs": (_i32, [_vp, _i32]),
     "cpm_host_alloc": (_i32, [_i64, _pp]),
     "cpm_host_free": (_i32, [_vp]),
     "cpm_host_register": (_i32, [_vp, _i64]),
@@ -97,6 +99,7 @@ SIGNATURES = {
     "cpm_fleet_copy_zones": (_i32, [_vp, _vp]),
     "cpm_run_day": (_i32, [_vp, _vp, C.POINTER(CDayOpts)]),
     "cpm_fleet_get_counts": (_i32, [_vp, _vp, _vp, C.POINTER(_d), C.POINTER(_i64)]),
+    "cpm_fleet_last_sampler": (_i32, [_vp, C.POINTER(_i32)]),
     "cpm_fleet_get_time_fixed": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "cpm_fleet_counts_device": (_i32, [_vp, _pp, C.POINTER(_i64)]),
     "cpm_sample_dataset": (_i32, [_vp, _vp, C.POINTER(CParams), _i64, _u64, _i32, _vp, _vp, C.POINTER(_d), C.POINTER(_i64)]),

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <chrono>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -130,6 +131,8 @@ struct cpm_ctx {
     HostKey hk_mean, hk_sd, hk_dist, hk_pdest, hk_state, hk_trans[4];
     bool cache_inputs = true;
     int64_t uploads_skipped = 0;
+    int64_t graph_replays = 0;               // passes replayed as an executable graph (small cities)
+    bool graphs = true;                      // cpm_ctx_set_graphs
     struct SweepState *sweep = nullptr;      // fleets and staging kept between cpm_sweep calls
     DevBuf traj_state, traj_trans, u[4], tmp, partials, scalars;
     // optional timing of the sampling kernel: one event pair per day (consecutive launches of the step kernel)
@@ -173,6 +176,10 @@ struct cpm_fleet {
     // perm: car ids grouped by bin; dest: (destination, rank) per slot; pos: per-slab {count, first position} rows;
     // tot: two padded per-destination arrival counter arrays (ping-pong over the steps); first_zone: per slab
     DevBuf perm[2], dest, pos, tot, first_zone, bcnt, bdrv, cnt_cur, start_tmp, cursor_tmp, lost_acc;
+    int32_t last_sampler = 0;   // CPM_SAMPLER_* the last day ran on
+    DevBuf cars_cnt;   // car-resident day kernel: occupancy before the first step [N+1] | net arrivals [S][N+1] | drivers [S][N+1]
+    // small cities: the launch sequence of a pass over this fleet, kept as an executable graph (graph_run)
+    struct PassGraph { cudaGraphExec_t exec = nullptr; uint64_t key = 0; int seen = 0; bool off = false; } pg;
 };
 
 struct Scalars {   // device-side scalar block of a fleet
@@ -646,8 +653,9 @@ extern "C" int32_t cpm_fleet_destroy(cpm_fleet *f)
     if (f->ctx->copy_st) cudaStreamSynchronize(f->ctx->copy_st);
     cudaStreamSynchronize(f->ctx->st);
     DevBuf *bufs[] = { &f->zone, &f->counts, &f->scalars, &f->norm_out, &f->perm[0], &f->perm[1], &f->dest, &f->pos, &f->bcnt,
-                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->tot, &f->first_zone, &f->lost_acc };
+                       &f->bdrv, &f->cnt_cur, &f->start_tmp, &f->cursor_tmp, &f->tot, &f->first_zone, &f->lost_acc, &f->cars_cnt };
     for (DevBuf *b : bufs) b->release();
+    if (f->pg.exec) cudaGraphExecDestroy(f->pg.exec);
     delete f;
     return CPM_OK;
 }
@@ -876,6 +884,66 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     return CPM_OK;
 }
 
+// car-resident sampler: the whole day in one launch (daycars.cu); per hour when the hour's std slab is still on its way up
+static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
+{
+    cpm_ctx *ctx = f->ctx;
+    const int64_t N = city->N, C = f->C, S = o->n_steps;
+    const size_t NB = (size_t)N + 1;
+    CarsGeom g;
+    if (!cars_geometry(N, C, o->with_time, &g)) return fail(CPM_ERR_ARG, "the car-resident sampler does not support this city size");
+    if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
+    TRY(f->cars_cnt.ensure((2 * (size_t)S + 1) * NB * 4));
+    CU(cudaMemsetAsync(f->cars_cnt.p, 0, (2 * (size_t)S + 1) * NB * 4, ctx->st));
+    Scalars *sc = f->scalars.as<Scalars>();
+    DayArgs a;
+    memset(&a, 0, sizeof a);
+    a.p_drive = city->p_drive.as<double>(); a.cdf = city->cdf.as<double>(); a.ldc = city->ldc; a.goff = city->goff; a.G = city->G;
+    a.gshift = 32 - ilog2(city->G);
+    a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
+    a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
+    a.N = N; a.T_tab = city->T; a.C = C; a.steps_per_hour = o->steps_per_hour; a.with_time = o->with_time;
+    a.pd_smem = g.pd_smem; a.cars_per_cta = g.cars_per_cta;
+    a.zone = f->zone.as<int32_t>();
+    a.cnt0 = f->cars_cnt.as<uint32_t>(); a.net = a.cnt0 + NB; a.drv = a.net + (size_t)S * NB;
+    a.rng = make_rng(o->rng, C);
+    a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo;
+    uint32_t *const cnt0 = a.cnt0;
+    const bool by_hour = ctx->step_wait != nullptr && o->with_time;
+    for (int64_t s0 = 0; s0 < S;) {
+        const int64_t hour = s0 / o->steps_per_hour;
+        int64_t n = S - s0;
+        if (by_hour) {
+            n = std::min<int64_t>(n, (hour + 1) * o->steps_per_hour - s0);
+            if (hour < ctx->n_step_wait) CU(cudaStreamWaitEvent(ctx->st, ctx->step_wait[hour], 0));
+        }
+        a.step0 = s0; a.n_steps = n;
+        TRY(profile_open(ctx, n));
+        LAUNCH(ctx, launch_day_cars(a, g, ctx->st));
+        TRY(profile_close(ctx));
+        a.cnt0 = nullptr;   // the occupancy before the day's first step is counted once
+        s0 += n;
+    }
+    LAUNCH(ctx, launch_cars_export_counts(cnt0, a.net, a.drv, (int)N, S, f->counts.as<uint32_t>(), f->counts.as<uint32_t>() + (size_t)N * S,
+                                          &sc->lost, ctx->st));
+    f->zone_valid = true; f->bucket_valid = false;
+    return CPM_OK;
+}
+
+// which sampler a day runs on: the car-resident kernel wherever it applies (AUTO), the bucket pair when asked for or when
+// the per-zone tables of the car-resident kernel do not fit shared memory, the trajectory-recording gather kernel otherwise
+static int32_t pick_sampler(const cpm_city *city, const cpm_fleet *f, int32_t want, int with_time, bool traj)
+{
+    if (traj || want == CPM_SAMPLER_GATHER || city->G <= 0) return CPM_SAMPLER_GATHER;
+    CarsGeom g;
+    const bool cars = cars_geometry(city->N, f->C, with_time, &g), bucket = bucket_supported(city->N, city->ldc);
+    if (want == CPM_SAMPLER_CARS) return cars ? CPM_SAMPLER_CARS : -1;
+    if (want == CPM_SAMPLER_BUCKET) return bucket ? CPM_SAMPLER_BUCKET : -1;
+    static const int prefer_bucket = getenv("CPM_PREFER_BUCKET") ? atoi(getenv("CPM_PREFER_BUCKET")) : 0;
+    if (cars && !(prefer_bucket && bucket)) return CPM_SAMPLER_CARS;
+    return bucket ? CPM_SAMPLER_BUCKET : CPM_SAMPLER_GATHER;
+}
+
 // Enqueues n_steps steps (no host sync).  Counts, driving-time sum and lost counter are reset first.
 static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj)
 {
@@ -884,7 +952,7 @@ static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o
     ARG(o->n_steps >= 1 && o->steps_per_hour >= 1);
     ARG((o->n_steps - 1) / o->steps_per_hour < city->T);
     ARG(o->rng.mode == CPM_RNG_PHILOX || o->rng.mode == CPM_RNG_INJECTED);
-    ARG(o->sampler == CPM_SAMPLER_AUTO || o->sampler == CPM_SAMPLER_GATHER || o->sampler == CPM_SAMPLER_BUCKET);
+    ARG(o->sampler == CPM_SAMPLER_AUTO || o->sampler == CPM_SAMPLER_GATHER || o->sampler == CPM_SAMPLER_BUCKET || o->sampler == CPM_SAMPLER_CARS);
     if (!city->have_pdrive || !city->have_cdf) return fail(CPM_ERR_STATE, "sampling needs p_drive and the p_dest CDF (build or set them first)");
     if (o->with_time && !city->have_inputs) return fail(CPM_ERR_STATE, "travel-time sampling needs datamatrix and distance_matrix_km");
     if (o->rng.mode == CPM_RNG_INJECTED) {
@@ -892,14 +960,18 @@ static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o
         if (o->with_time) ARG(o->rng.u_time && (traj == nullptr || o->rng.u_dist));
     }
     const int64_t N = city->N;
-    const bool can_bucket = traj == nullptr && city->G > 0 && bucket_supported(N, city->ldc);
-    if (o->sampler == CPM_SAMPLER_BUCKET && !can_bucket)
-        return fail(CPM_ERR_ARG, "the bucket sampler needs N + 1 <= 65535, a CDF row that fits shared memory, and no trajectory recording");
-    const bool use_bucket = can_bucket && o->sampler != CPM_SAMPLER_GATHER;
+    const int32_t sampler = (traj != nullptr && o->sampler != CPM_SAMPLER_AUTO && o->sampler != CPM_SAMPLER_GATHER)
+                                ? -1 : pick_sampler(city, f, o->sampler, o->with_time, traj != nullptr);
+    if (sampler < 0)
+        return fail(CPM_ERR_ARG, "the bucket and car-resident samplers need N + 1 <= 65535, per-zone tables that fit shared memory, "
+                                 "a guide table, and no trajectory recording");
     TRY(f->counts.ensure(2 * (size_t)N * o->n_steps * sizeof(uint32_t)));
     f->counts_N = N; f->counts_steps = o->n_steps;
     CU(cudaMemsetAsync(f->scalars.p, 0, sizeof(Scalars), ctx->st));
-    TRY(use_bucket ? day_bucket(city, f, o) : day_gather(city, f, o, traj));
+    f->last_sampler = sampler;
+    if (sampler == CPM_SAMPLER_CARS) TRY(day_cars(city, f, o));
+    else if (sampler == CPM_SAMPLER_BUCKET) TRY(day_bucket(city, f, o));
+    else TRY(day_gather(city, f, o, traj));
     Scalars *sc = f->scalars.as<Scalars>();
     if (o->with_time) LAUNCH(ctx, launch_finalize_time(&sc->t_hi, &sc->t_lo, &sc->time_sum, ctx->st));
     return CPM_OK;
@@ -929,6 +1001,12 @@ extern "C" int32_t cpm_fleet_get_counts(cpm_fleet *f, int64_t *parking, int64_t 
     if (n_lost) *n_lost = (int64_t)sc.lost;
     return CPM_OK;
 }
+extern "C" int32_t cpm_fleet_last_sampler(cpm_fleet *f, int32_t *sampler)
+{
+    ARG(f && sampler);
+    *sampler = f->last_sampler;
+    return CPM_OK;
+}
 extern "C" int32_t cpm_fleet_get_time_fixed(cpm_fleet *f, int64_t *seconds, int64_t *frac32)
 {
     ARG(f && seconds && frac32);
@@ -947,6 +1025,67 @@ extern "C" int32_t cpm_fleet_counts_device(cpm_fleet *f, void **dev_ptr, int64_t
     if (f->counts_steps == 0) return fail(CPM_ERR_STATE, "no day has been run on this fleet");
     *dev_ptr = f->counts.p;
     *n_elems = 2 * f->counts_N * f->counts_steps;
+    return CPM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small cities: a pass is ~110 launches of kernels that take 2-4 us each, so the host's launch rate (4-5 us per launch)
+// sets the pace, not the GPU.  graph_run captures the launch sequence of `body` (everything it enqueues on the context's
+// stream and the streams forked from it) and replays it as one executable graph.  The first pass of a shape runs
+// directly (it allocates), the second instantiates the graph, every later one re-captures (cheap: nothing is launched)
+// and patches the executable graph's kernel arguments in place -- seeds, parameters and pointers may all differ from
+// pass to pass, only the shape of the sequence must not.  Same kernels, same arguments, same order: results are
+// identical to the direct path.  CPM_GRAPH_MAX_CARS (default 300,000; 0 = never) bounds the fleets it is used for.
+// ------------------------------------------------------------------------------------------------
+static int64_t graph_max_cars()
+{
+    static const int64_t v = getenv("CPM_GRAPH_MAX_CARS") ? atoll(getenv("CPM_GRAPH_MAX_CARS")) : 300000;
+    return v;
+}
+
+static int32_t graph_run(cpm_fleet *f, uint64_t key, const std::function<int32_t()> &body)
+{
+    cpm_ctx *ctx = f->ctx;
+    cpm_fleet::PassGraph &pg = f->pg;
+    const bool eligible = ctx->graphs && !pg.off && f->C <= graph_max_cars() && !ctx->profiling && ctx->st != nullptr &&
+                          ctx->st != cudaStreamLegacy && ctx->st != cudaStreamPerThread;
+    if (!eligible) return body();
+    if (pg.key != key) {
+        if (pg.exec) { cudaGraphExecDestroy(pg.exec); pg.exec = nullptr; }
+        pg.key = key; pg.seen = 0;
+    }
+    if (pg.seen++ == 0) return body();   // first pass of this shape: direct (allocations, one-time attribute calls)
+    static const bool dbg = getenv("CPM_GRAPH_DEBUG") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = dbg ? now() : 0.0;
+    if (cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); pg.off = true; return body(); }
+    const int64_t launches0 = ctx->launches;
+    const int32_t rc = body();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(ctx->st, &graph);
+    const double t1 = dbg ? now() : 0.0;
+    if (rc != CPM_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    bool ok = e_end == cudaSuccess && graph != nullptr;
+    if (ok && pg.exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(pg.exec, graph, &info) != cudaSuccess) {   // the sequence changed shape: build it anew
+            cudaGetLastError();
+            cudaGraphExecDestroy(pg.exec); pg.exec = nullptr;
+        }
+    }
+    if (ok && !pg.exec) ok = cudaGraphInstantiate(&pg.exec, graph, 0) == cudaSuccess;
+    const double t2 = dbg ? now() : 0.0;
+    if (graph) cudaGraphDestroy(graph);
+    if (ok) ok = cudaGraphLaunch(pg.exec, ctx->st) == cudaSuccess;
+    if (dbg) fprintf(stderr, "[graph] capture %.0f us, update/instantiate %.0f us, destroy+launch %.0f us\n", t1 - t0, t2 - t1, now() - t2);
+    if (!ok) {   // nothing ran: capture is unavailable for this sequence here -- run it directly, now and from now on
+        cudaGetLastError();
+        if (pg.exec) { cudaGraphExecDestroy(pg.exec); pg.exec = nullptr; }
+        pg.off = true;
+        ctx->launches = launches0;
+        return body();
+    }
+    ++ctx->graph_replays;
     return CPM_OK;
 }
 
@@ -996,7 +1135,8 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     // initializestates (main.jl:88) and the grouping of the cars by zone do not depend on the tables: second stream as well
     LAUNCH(ctx, launch_fleet_init(fleet->zone.as<int32_t>(), fleet->C, cars_per_zone, 0, ctx->aux_st));
     fleet->car_offset = 0; fleet->zone_valid = true; fleet->bucket_valid = false;
-    if (sampler != CPM_SAMPLER_GATHER && city->G > 0 && bucket_supported(N, city->ldc)) TRY(fleet_bucketize_async(fleet, N, city->ldc, T > 1 ? 0 : 1, ctx->aux_st));
+    if (pick_sampler(city, fleet, sampler, T > 1 ? 0 : 1, false) == CPM_SAMPLER_BUCKET)
+        TRY(fleet_bucketize_async(fleet, N, city->ldc, T > 1 ? 0 : 1, ctx->aux_st));
     CU(cudaEventRecord(ctx->ev_aux[1], ctx->aux_st));
     CU(cudaStreamWaitEvent(ctx->st, ctx->ev_aux[1], 0));
     cpm_day_opts o;
@@ -1019,6 +1159,15 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     TRY(rc_day);
     TRY(normalise_async(fleet, N, T, fleet->C));                                            // saveresults.jl:6-28
     return CPM_OK;
+}
+
+// what fixes the shape of a pass's launch sequence (kind: 1 dataset pass, 2 sweep set)
+static uint64_t pass_key(const cpm_city *city, const cpm_fleet *fleet, int32_t sampler, int kind)
+{
+    uint64_t k = 0xcbf29ce484222325ull;
+    const int64_t v[] = {city->N, city->T, fleet->C, sampler, kind, city->G, city->ldc, city->have_msd ? 1 : 0};
+    for (int64_t x : v) { k ^= (uint64_t)x; k *= 0x100000001b3ull; }
+    return k | 1ull;
 }
 
 static int32_t sample_dataset_collect(cpm_city *city, cpm_fleet *fleet, double *parking, double *traffic, double *A_drive,
@@ -1045,7 +1194,8 @@ extern "C" int32_t cpm_sample_dataset(cpm_city *city, cpm_fleet *fleet, const cp
 {
     ARG(city && fleet && pr && cars_per_zone >= 1);
     TRY(use(fleet->ctx));
-    TRY(sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, nullptr));
+    TRY(graph_run(fleet, pass_key(city, fleet, sampler, 1),
+                  [&]() { return sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, nullptr); }));
     return sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);
 }
 
@@ -1091,8 +1241,17 @@ extern "C" int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, con
     CU(cudaEventRecord(ctx->ev_copy[1], ctx->copy_st));
     city->have_inputs = true;
     city_invalidate(city);
-    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[0], 0));
-    int32_t rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, ctx->ev_hour.data());
+    int32_t rc;
+    if (ctx->graphs && fleet->C <= graph_max_cars()) {
+        // small city: the whole upload is a few hundred microseconds, the pass is launch-bound -- wait for all of it and
+        // replay the pass as a graph (graph_run) instead of pipelining hour slabs
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[1], 0));
+        rc = graph_run(fleet, pass_key(city, fleet, sampler, 1),
+                       [&]() { return sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, nullptr); });
+    } else {
+        CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[0], 0));
+        rc = sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, ctx->ev_hour.data());
+    }
     if (rc != CPM_OK) { cudaStreamSynchronize(ctx->copy_st); cudaStreamSynchronize(ctx->st); return rc; }
     return sample_dataset_collect(city, fleet, parking, traffic, A_drive, n_lost);   // the caller may reuse its buffers after this
 }
@@ -1209,7 +1368,7 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
         }
     }
     TRY(city_alloc_cdf(city));
-    const bool bucket = city->G > 0 && bucket_supported(N, city->ldc);
+    const bool bucket = pick_sampler(city, w->base, CPM_SAMPLER_AUTO, 1, false) == CPM_SAMPLER_BUCKET;
     // the initial state: uploaded and grouped by zone once, as long as the caller passes the same unchanged array
     const bool same_init = hk_match(ctx, w->init_key, initial_zones, (size_t)C * sizeof(int64_t)) && w->base->zone_valid &&
                            (!bucket || (w->base->bucket_valid && w->base->bucket_N == N));
@@ -1248,15 +1407,19 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
             rc = city_build_pdestin_async(city, pr.e_dest, false);
             have_e_dest = true; cur_e_dest = pr.e_dest;
         }
-        if (rc == CPM_OK) rc = city_build_pdrive_async(city, pr.p_min, pr.p_max, pr.e_drive);   // mean_sum cached
-        if (rc == CPM_OK) rc = cpm_fleet_copy_zones(work, w->base);                                // README.md:1014,1549
         cpm_day_opts o;
         memset(&o, 0, sizeof o);
         o.n_steps = T; o.steps_per_hour = 1; o.with_time = 1; o.sampler = CPM_SAMPLER_AUTO;
         o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
         o.rng.stream = streams ? streams[p] : (uint32_t)(2 + p);
-        if (rc == CPM_OK) rc = run_day_async(city, work, &o, nullptr);
-        if (rc == CPM_OK) rc = normalise_async(work, N, T, C);
+        // one set = p_drive from the cached row sums, a copy of the initial state, one day, the normalisation: the same
+        // launch sequence for every set, replayed as a graph when the city is small enough to be launch-bound
+        if (rc == CPM_OK) rc = graph_run(work, pass_key(city, work, o.sampler, 2), [&]() -> int32_t {
+            TRY(city_build_pdrive_async(city, pr.p_min, pr.p_max, pr.e_drive));   // mean_sum cached
+            TRY(cpm_fleet_copy_zones(work, w->base));                             // README.md:1014,1549
+            TRY(run_day_async(city, work, &o, nullptr));
+            return normalise_async(work, N, T, C);
+        });
         if (rc != CPM_OK) break;
         const double *d_parking = work->norm_out.as<double>();
         const unsigned long long *d_tc = reinterpret_cast<const unsigned long long *>(d_parking + (size_t)N * T + T);
@@ -1314,6 +1477,19 @@ extern "C" int32_t cpm_ctx_uploads_skipped(cpm_ctx *ctx, int64_t *count)
 {
     ARG(ctx && count);
     *count = ctx->uploads_skipped;
+    return CPM_OK;
+}
+
+extern "C" int32_t cpm_ctx_set_graphs(cpm_ctx *ctx, int32_t enabled)
+{
+    ARG(ctx != nullptr);
+    ctx->graphs = enabled != 0;
+    return CPM_OK;
+}
+extern "C" int32_t cpm_ctx_graph_replays(cpm_ctx *ctx, int64_t *count)
+{
+    ARG(ctx && count);
+    *count = ctx->graph_replays;
     return CPM_OK;
 }
 

@@ -62,6 +62,32 @@ int sampler_grid(int64_t C);
 int launch_step_gather(const StepArgs &a, cudaStream_t st);
 int launch_reduce_partials(const double *partials, int n, double *out, cudaStream_t st);
 
+// ---- daycars.cu -------------------------------------------------------------------------------
+// the car-resident day kernel: one launch = steps [step0, step0 + n_steps) of a day for all cars
+struct CarsGeom {
+    int n_ctas, threads;
+    int cars_per_cta;          // car slots a CTA keeps in shared memory (a multiple of 4 * threads)
+    int pd_smem;               // the hour's p_drive column is staged in shared memory
+    size_t smem;
+};
+struct DayArgs {
+    const double *p_drive; const double *cdf; int64_t ldc; int32_t goff, G, gshift; const uint8_t *rowzero; const double *dm;
+    const double2 *msd;        // nullable: (mean, std) pairs
+    int64_t N, T_tab, C;
+    int64_t step0, n_steps, steps_per_hour;
+    int32_t with_time, pd_smem, cars_per_cta;
+    int32_t *zone;             // [C] in/out: 1-based zone, 0 = lost
+    uint32_t *cnt0;            // nullable: [N+1] += occupancy of every bin before step0 (bin N = lost cars)
+    uint32_t *net;             // [day steps][N+1] += net arrivals per bin and step (two's complement)
+    uint32_t *drv;             // [day steps][N+1] += driving cars per origin and step
+    RngDev rng;
+    unsigned long long *t_hi, *t_lo;
+};
+bool cars_geometry(int64_t N, int64_t C, int with_time, CarsGeom *g);
+int launch_day_cars(const DayArgs &a, const CarsGeom &g, cudaStream_t st);
+int launch_cars_export_counts(const uint32_t *cnt0, const uint32_t *net, const uint32_t *drv, int N, int64_t n_steps,
+                              uint32_t *parking, uint32_t *driving, unsigned long long *lost, cudaStream_t st);
+
 // ---- bucket.cu --------------------------------------------------------------------------------
 constexpr int kTotStride = 64;   // uint32 words between two per-destination arrival counters: 256 B, one L2 slice each
 struct BucketGeom {

@@ -88,6 +88,17 @@ class Context:
         L.check(L.lib().cpm_ctx_uploads_skipped(self._h, C.byref(n)))
         return n.value
 
+    def set_graphs(self, enabled: bool):
+        """Small cities: replay repeated passes as CUDA graphs (default on)."""
+        L.check(L.lib().cpm_ctx_set_graphs(self._h, int(bool(enabled))))
+
+    @property
+    def graph_replays(self) -> int:
+        """Passes over small cities that ran as a replayed CUDA graph (cpm.h: cpm_ctx_graph_replays)."""
+        n = C.c_int64()
+        L.check(L.lib().cpm_ctx_graph_replays(self._h, C.byref(n)))
+        return n.value
+
     def profile_begin(self):
         L.check(L.lib().cpm_ctx_profile_begin(self._h))
 
@@ -244,6 +255,13 @@ class Fleet:
         ts, lost = C.c_double(), C.c_int64()
         L.check(L.lib().cpm_fleet_get_counts(self._h, _ptr(parking), _ptr(driving), C.byref(ts), C.byref(lost)))
         return parking, driving, ts.value, lost.value
+
+    @property
+    def last_sampler(self) -> int:
+        """SAMPLER_GATHER / SAMPLER_BUCKET / SAMPLER_CARS: what the last day ran on (what SAMPLER_AUTO resolved to)."""
+        v = C.c_int32()
+        L.check(L.lib().cpm_fleet_last_sampler(self._h, C.byref(v)))
+        return v.value
 
     def time_fixed(self):
         """(whole seconds, 2^-32 s units) of the last day's driving-time sum: exact integers."""

@@ -88,6 +88,13 @@ int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int64_t *step_
  * callers that edit those arrays in place between calls.  cpm_ctx_uploads_skipped counts the hits. */
 int32_t cpm_ctx_set_input_cache(cpm_ctx *ctx, int32_t enabled);
 int32_t cpm_ctx_uploads_skipped(cpm_ctx *ctx, int64_t *count);
+/* Small cities (fleets of at most CPM_GRAPH_MAX_CARS cars, default 300,000; 0 = never): from the third pass of the same
+ * shape on, cpm_sample_dataset, cpm_sample_dataset_host and every set of cpm_sweep replay their launch sequence as one
+ * executable CUDA graph whose kernel arguments are patched in place (same kernels, same arguments, same results; the
+ * host's launch rate no longer bounds the pass).  cpm_ctx_graph_replays counts the passes that ran that way;
+ * cpm_ctx_set_graphs(ctx, 0) keeps every pass on direct launches (default: enabled). */
+int32_t cpm_ctx_set_graphs(cpm_ctx *ctx, int32_t enabled);
+int32_t cpm_ctx_graph_replays(cpm_ctx *ctx, int64_t *count);
 /* pinned host memory for callers that want full-rate PCIe copies */
 int32_t cpm_host_alloc(int64_t bytes, void **out);
 int32_t cpm_host_free(void *p);
@@ -204,7 +211,7 @@ int32_t cpm_fleet_set_zones(cpm_fleet *fleet, const int64_t *zones);
 int32_t cpm_fleet_get_zones(cpm_fleet *fleet, int64_t *zones_out);
 int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src);
 
-enum { CPM_SAMPLER_AUTO = 0, CPM_SAMPLER_GATHER = 1, CPM_SAMPLER_BUCKET = 2 };
+enum { CPM_SAMPLER_AUTO = 0, CPM_SAMPLER_GATHER = 1, CPM_SAMPLER_BUCKET = 2, CPM_SAMPLER_CARS = 3 };
 
 typedef struct cpm_day_opts {
     int64_t n_steps;        /* steps to run (T-1 for the IVP, T for a resampling day)          */
@@ -224,6 +231,8 @@ int32_t cpm_fleet_get_counts(cpm_fleet *fleet, int64_t *parking, int64_t *drivin
 /* the driving-time sum of the last cpm_run_day in fixed point: whole seconds and 2^-32 s units (exact integers, so a
  * multi-GPU host adds them with an integer all-reduce and gets the unsplit run's value bit for bit) */
 int32_t cpm_fleet_get_time_fixed(cpm_fleet *fleet, int64_t *seconds, int64_t *frac32);
+/* which sampler (CPM_SAMPLER_GATHER / BUCKET / CARS) the fleet's last day ran on: what CPM_SAMPLER_AUTO resolved to */
+int32_t cpm_fleet_last_sampler(cpm_fleet *fleet, int32_t *sampler);
 /* device pointer to the uint32 [2][N,n_steps] count block (parking then driving), for an
  * in-place NCCL all-reduce by the host when one city's cars are split over GPUs */
 int32_t cpm_fleet_counts_device(cpm_fleet *fleet, void **dev_ptr, int64_t *n_elems);

@@ -9,7 +9,7 @@ Everything is compared exactly: counts, driving counts, lost cars and final zone
 import numpy as np
 import pytest
 
-from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_GATHER, City, Fleet, Rng
+from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_CARS, SAMPLER_GATHER, City, Fleet, Rng
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -70,7 +70,7 @@ def test_full_size_tables_guide_and_sampling_against_oracle(ctx, N, cpz, density
     #      could flip a `u <= p_drive` decision; the table comparison above is where p_drive is checked) ----
     city.set_pdrive(pd)
     zone0 = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
-    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER):
+    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER, SAMPLER_CARS):
         f = Fleet(ctx, C).set_zones(zone0)
         zone_o = zone0.copy()
         for stream, n_steps, with_time in [(0, T - 1, False), (1, T, True)]:
@@ -114,7 +114,7 @@ def test_full_size_injected_variates_with_sentinels(ctx, N, cpz):
                         O.Rng(mode="injected", u_drive=us[0], u_dest=us[1], u_time=us[2], u_dist=us[3]), True)
     assert want[3] > 0                                           # some cars were lost on the way
     dev = [_dev(u) for u in us]
-    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER):
+    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER, SAMPLER_CARS):
         f = Fleet(ctx, C).set_zones(zone0)
         f.run_day(city, n_steps, with_time=True, sampler=sampler,
                   rng=Rng(mode="injected", u_drive=dev[0][1], u_dest=dev[1][1], u_time=dev[2][1], u_dist=dev[3][1]))

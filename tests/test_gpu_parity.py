@@ -297,8 +297,8 @@ def test_sample_dataset_matches_oracle_pipeline(ctx, N, cpz, density):
 @pytest.mark.parametrize("N,cpz,Tn", [(1, 1, 24), (1, 7, 24), (2, 1, 24), (3, 2, 2), (4, 5, 1), (2, 33, 3)])
 def test_sample_dataset_degenerate_shapes(ctx, N, cpz, Tn):
     """One zone (every trip is a 5-minute same-zone trip or no trip at all), one car, one hour (no IVP steps at all):
-    the whole pass against the oracle, both samplers."""
-    from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_GATHER
+    the whole pass against the oracle, every sampler."""
+    from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_CARS, SAMPLER_GATHER
     C = N * cpz
     dm, dist = synth_city(N, Tn, seed=N * 100 + cpz, density=1.0)
     pd = O.createpdrive(dm, dist, N, T=Tn, p_min=0.1, p_max=0.9, e_drive=0.5)
@@ -310,7 +310,7 @@ def test_sample_dataset_degenerate_shapes(ctx, N, cpz, Tn):
     tot = dr0.sum(axis=0).astype(np.float64)
     with np.errstate(invalid="ignore", divide="ignore"):
         traffic0 = (tot - tot.min()) / (tot.max() - tot.min())            # 0/0 -> NaN when every hour has the same count
-    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER):
+    for sampler in (SAMPLER_BUCKET, SAMPLER_GATHER, SAMPLER_CARS):
         city = City(ctx, N, Tn).upload(dm, dist)
         fleet = Fleet(ctx, C)
         parking, traffic, A, lost = sample_dataset(city, fleet, cars_per_zone=cpz, seed=5, sampler=sampler)
@@ -359,9 +359,10 @@ def test_philox_vs_stream_monte_carlo_chi_square(ctx):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# bucket sampler (cars grouped by zone, CDF rows staged in shared memory) == gather sampler == oracle
+# bucket sampler (cars grouped by zone, CDF rows staged in shared memory) == car-resident day kernel == gather sampler
+# == oracle
 # ---------------------------------------------------------------------------------------------------------
-from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_GATHER  # noqa: E402
+from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_CARS, SAMPLER_GATHER  # noqa: E402
 
 
 def _dev(u):
@@ -382,7 +383,7 @@ def test_bucket_sampler_bit_exact(ctx, N, cpz, density, skew, mode):
     zone0 = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
     if skew:   # most cars start in one zone: a bucket far larger than one work item (2,048 cars)
         zone0[: C * 3 // 4] = 2
-    fb, fg = Fleet(ctx, C), Fleet(ctx, C)
+    fb, fg, fc = Fleet(ctx, C), Fleet(ctx, C), Fleet(ctx, C)
     zone_o = zone0.copy()
     keep = []
     for stream, n_steps, with_time in [(0, T - 1, False), (1, T, True)]:
@@ -397,24 +398,26 @@ def test_bucket_sampler_bit_exact(ctx, N, cpz, density, skew, mode):
             dev = [_dev(u) for u in us]; keep.append(dev)
             rb = rg = Rng(mode="injected", u_drive=dev[0][1], u_dest=dev[1][1], u_time=dev[2][1], u_dist=dev[3][1])
         if stream == 0:
-            fb.set_zones(zone0); fg.set_zones(zone0)
+            fb.set_zones(zone0); fg.set_zones(zone0); fc.set_zones(zone0)
         fb.run_day(city, n_steps, with_time=with_time, rng=rb, sampler=SAMPLER_BUCKET)
         fg.run_day(city, n_steps, with_time=with_time, rng=rg, sampler=SAMPLER_GATHER)
+        fc.run_day(city, n_steps, with_time=with_time, rng=rg, sampler=SAMPLER_CARS)
         pk0, dr0, ts0, lost0 = O.day_counts(zone_o, N, T, n_steps, 1, pd, px, dm, dist, r_o, with_time)
-        for f in (fb, fg):
+        for f in (fb, fg, fc):
             pk, dr, ts, lost = f.counts()
             np.testing.assert_array_equal(pk, pk0)
             np.testing.assert_array_equal(dr, dr0)
             assert lost == lost0
             np.testing.assert_allclose(ts, ts0, rtol=TIME_RTOL)
             np.testing.assert_array_equal(f.zones(), zone_o)
-        assert fb.counts()[2] == fg.counts()[2]                  # fixed-point time sum: identical across samplers
+        assert fb.counts()[2] == fg.counts()[2] == fc.counts()[2]   # fixed-point time sum: identical across samplers
         if mode == "injected" and stream == 0:
             assert lost0 > 0
-    city.close(); fb.close(); fg.close()
+    city.close(); fb.close(); fg.close(); fc.close()
 
 
-def test_bucket_sampler_nan_rows_and_lost_bin(ctx):
+@pytest.mark.parametrize("sampler", [SAMPLER_BUCKET, SAMPLER_CARS])
+def test_bucket_sampler_nan_rows_and_lost_bin(ctx, sampler):
     """edge-case city: NaN rows (cars get lost), all-zero rows (cars stay), NaN p_drive rows (never drive)"""
     dm, dist = edge_case_city(T)
     N, cpz = 6, 700
@@ -425,7 +428,7 @@ def test_bucket_sampler_nan_rows_and_lost_bin(ctx):
     pd2 = np.asfortranarray(np.where(pd == 0, 0.3, pd)); city.set_pdrive(pd2)
     zone_o = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
     f = Fleet(ctx, C).set_zones(zone_o)
-    f.run_day(city, T, with_time=True, rng=Rng(seed=4, stream=1), sampler=SAMPLER_BUCKET)
+    f.run_day(city, T, with_time=True, rng=Rng(seed=4, stream=1), sampler=sampler)
     pk0, dr0, ts0, lost0 = O.day_counts(zone_o, N, T, T, 1, pd2, px, dm, dist, O.Rng(mode="philox", seed=4, stream=1), True)
     pk, dr, ts, lost = f.counts()
     assert lost0 > 0 and lost == lost0
@@ -436,7 +439,8 @@ def test_bucket_sampler_nan_rows_and_lost_bin(ctx):
     city.close(); f.close()
 
 
-def test_bucket_sampler_per_minute_steps_and_odd_sizes(ctx):
+@pytest.mark.parametrize("sampler", [SAMPLER_BUCKET, SAMPLER_CARS])
+def test_bucket_sampler_per_minute_steps_and_odd_sizes(ctx, sampler):
     N, cpz, sph = 37, 111, 3      # odd N: CDF rows are padded to 16 doubles for the TMA bulk copy
     C = N * cpz
     dm, dist = synth_city(N, T, seed=13, density=1.0)
@@ -444,7 +448,7 @@ def test_bucket_sampler_per_minute_steps_and_odd_sizes(ctx):
     city = City(ctx, N, T).upload(dm, dist).set_pdrive(pd).set_pdest(px)
     zone_o = np.repeat(np.arange(1, N + 1), cpz).astype(np.int64)
     f = Fleet(ctx, C).init(cpz)
-    f.run_day(city, T * sph, with_time=True, steps_per_hour=sph, rng=Rng(seed=6, stream=2), sampler=SAMPLER_BUCKET)
+    f.run_day(city, T * sph, with_time=True, steps_per_hour=sph, rng=Rng(seed=6, stream=2), sampler=sampler)
     pk0, dr0, ts0, _ = O.day_counts(zone_o, N, T, T * sph, sph, pd, px, dm, dist, O.Rng(mode="philox", seed=6, stream=2), True)
     pk, dr, ts, _ = f.counts()
     np.testing.assert_array_equal(pk, pk0)

@@ -4,7 +4,7 @@ CDF monotonicity; plus the large-N kernel shape (512-thread CTAs) against the ga
 import numpy as np
 import pytest
 
-from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_GATHER, City, Fleet, Rng, sample_dataset
+from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_CARS, SAMPLER_GATHER, City, Fleet, Rng, sample_dataset
 
 pytestmark = pytest.mark.gpu
 T = 24
@@ -40,12 +40,13 @@ def test_cfg2_full_size_properties(ctx):
     # determinism, and bucket == gather (identical draws: keyed by car id and step, not by processing order)
     pk2, dr2, ts2, _, zones2 = _day(ctx, city, C, cpz, SAMPLER_BUCKET)
     assert np.array_equal(pk, pk2) and np.array_equal(dr, dr2) and ts == ts2 and np.array_equal(zones, zones2)
-    pk3, dr3, ts3, _, zones3 = _day(ctx, city, C, cpz, SAMPLER_GATHER)
-    assert np.array_equal(pk, pk3) and np.array_equal(dr, dr3) and ts == ts3 and np.array_equal(zones, zones3)
+    for other in (SAMPLER_GATHER, SAMPLER_CARS):
+        pk3, dr3, ts3, _, zones3 = _day(ctx, city, C, cpz, other)
+        assert np.array_equal(pk, pk3) and np.array_equal(dr, dr3) and ts == ts3 and np.array_equal(zones, zones3)
     # cars split over two "ranks" with a global Philox counter: counts add up to the unsplit run (what NCCL all-reduces)
     h = C // 2 + 12345
     a = _day(ctx, city, h, cpz, SAMPLER_BUCKET, car_offset=0, zones=np.repeat(np.arange(1, N + 1), cpz)[:h])
-    b = _day(ctx, city, C - h, cpz, SAMPLER_BUCKET, car_offset=h, zones=np.repeat(np.arange(1, N + 1), cpz)[h:])
+    b = _day(ctx, city, C - h, cpz, SAMPLER_CARS, car_offset=h, zones=np.repeat(np.arange(1, N + 1), cpz)[h:])
     assert np.array_equal(a[0] + b[0], pk) and np.array_equal(a[1] + b[1], dr)
     np.testing.assert_allclose(a[2] + b[2], ts, rtol=1e-13)
     # the sampling CDF: rows are non-decreasing and end at 1 (or are all-zero)
@@ -78,9 +79,10 @@ def test_large_n_kernel_shape_matches_gather(ctx, N, cpz):
     zones0 = np.repeat(np.arange(1, N + 1), cpz)
     zones0[: C // 3] = 7                                         # skew: one zone far larger than a slab
     a = _day(ctx, city, C, cpz, SAMPLER_BUCKET, zones=zones0, n_steps=12)
-    b = _day(ctx, city, C, cpz, SAMPLER_GATHER, zones=zones0, n_steps=12)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
-    assert np.array_equal(a[4], b[4]) and (a[0].sum(axis=0) + 0 == C).all()
+    for other in (SAMPLER_GATHER, SAMPLER_CARS):
+        b = _day(ctx, city, C, cpz, other, zones=zones0, n_steps=12)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+        assert np.array_equal(a[4], b[4]) and (a[0].sum(axis=0) + 0 == C).all()
     city.close()
 
 
@@ -99,4 +101,10 @@ def test_cfg5_table_shape_small_fleet(ctx):
     c = g.counts() + (g.zones(),)
     assert np.array_equal(b[0], c[0]) and np.array_equal(b[1], c[1]) and b[2] == c[2] and np.array_equal(b[4], c[4])
     assert (b[0].sum(axis=0) == C).all() and a[3] == 0
-    f.close(); g.close(); city.close()
+    d = _day(ctx, city, C, cpz, SAMPLER_CARS, n_steps=8 * sph)   # the car-resident kernel at this table size (_day uses steps_per_hour 1)
+    assert np.array_equal(a[0], d[0]) and np.array_equal(a[1], d[1]) and a[2] == d[2] and np.array_equal(a[4], d[4])
+    h = Fleet(ctx, C).init(cpz)
+    h.run_day(city, 8 * sph, with_time=True, steps_per_hour=sph, sampler=SAMPLER_CARS, rng=Rng(seed=1, stream=1))
+    e = h.counts() + (h.zones(),)
+    assert np.array_equal(b[0], e[0]) and np.array_equal(b[1], e[1]) and b[2] == e[2] and np.array_equal(b[4], e[4])
+    f.close(); g.close(); h.close(); city.close()
