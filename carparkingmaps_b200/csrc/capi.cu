@@ -885,7 +885,7 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
 }
 
 // car-resident sampler: the whole day in one launch (daycars.cu); per hour when the hour's std slab is still on its way up
-static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
+static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, bool want_counts)
 {
     cpm_ctx *ctx = f->ctx;
     const int64_t N = city->N, C = f->C, S = o->n_steps;
@@ -893,8 +893,10 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     CarsGeom g;
     if (!cars_geometry(N, C, o->with_time, &g)) return fail(CPM_ERR_ARG, "the car-resident sampler does not support this city size");
     if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
-    TRY(f->cars_cnt.ensure((2 * (size_t)S + 1) * NB * 4));
-    CU(cudaMemsetAsync(f->cars_cnt.p, 0, (2 * (size_t)S + 1) * NB * 4, ctx->st));
+    if (want_counts) {
+        TRY(f->cars_cnt.ensure((2 * (size_t)S + 1) * NB * 4));
+        CU(cudaMemsetAsync(f->cars_cnt.p, 0, (2 * (size_t)S + 1) * NB * 4, ctx->st));
+    }
     Scalars *sc = f->scalars.as<Scalars>();
     DayArgs a;
     memset(&a, 0, sizeof a);
@@ -904,8 +906,11 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
     a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
     a.N = N; a.T_tab = city->T; a.C = C; a.steps_per_hour = o->steps_per_hour; a.with_time = o->with_time;
     a.pd_smem = g.pd_smem; a.cars_per_cta = g.cars_per_cta;
+    { static const int pf = getenv("CPM_CARS_PREFETCH") ? atoi(getenv("CPM_CARS_PREFETCH")) : 0; a.prefetch = pf; }
     a.zone = f->zone.as<int32_t>();
-    a.cnt0 = f->cars_cnt.as<uint32_t>(); a.net = a.cnt0 + NB; a.drv = a.net + (size_t)S * NB;
+    a.counts = want_counts ? 1 : 0;
+    if (want_counts) { a.cnt0 = f->cars_cnt.as<uint32_t>(); a.net = a.cnt0 + NB; a.drv = a.net + (size_t)S * NB; }
+    else a.lost_visits = &sc->lost;   // the scalar block was zeroed at the start of the day
     a.rng = make_rng(o->rng, C);
     a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo;
     uint32_t *const cnt0 = a.cnt0;
@@ -924,8 +929,9 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
         a.cnt0 = nullptr;   // the occupancy before the day's first step is counted once
         s0 += n;
     }
-    LAUNCH(ctx, launch_cars_export_counts(cnt0, a.net, a.drv, (int)N, S, f->counts.as<uint32_t>(), f->counts.as<uint32_t>() + (size_t)N * S,
-                                          &sc->lost, ctx->st));
+    if (want_counts)
+        LAUNCH(ctx, launch_cars_export_counts(cnt0, a.net, a.drv, (int)N, S, f->counts.as<uint32_t>(), f->counts.as<uint32_t>() + (size_t)N * S,
+                                              &sc->lost, ctx->st));
     f->zone_valid = true; f->bucket_valid = false;
     return CPM_OK;
 }
@@ -945,7 +951,9 @@ static int32_t pick_sampler(const cpm_city *city, const cpm_fleet *f, int32_t wa
 }
 
 // Enqueues n_steps steps (no host sync).  Counts, driving-time sum and lost counter are reset first.
-static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj)
+// `want_counts` = false (the IVP of a dataset pass: only the end state and the lost-car visits are used) lets the
+// car-resident sampler skip the per-zone rows; the other samplers count regardless.
+static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj, bool want_counts = true)
 {
     cpm_ctx *ctx = f->ctx;
     ARG(city->ctx == ctx);
@@ -969,7 +977,7 @@ static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o
     f->counts_N = N; f->counts_steps = o->n_steps;
     CU(cudaMemsetAsync(f->scalars.p, 0, sizeof(Scalars), ctx->st));
     f->last_sampler = sampler;
-    if (sampler == CPM_SAMPLER_CARS) TRY(day_cars(city, f, o));
+    if (sampler == CPM_SAMPLER_CARS) TRY(day_cars(city, f, o, want_counts));
     else if (sampler == CPM_SAMPLER_BUCKET) TRY(day_bucket(city, f, o));
     else TRY(day_gather(city, f, o, traj));
     Scalars *sc = f->scalars.as<Scalars>();
@@ -1145,7 +1153,7 @@ static int32_t sample_dataset_enqueue(cpm_city *city, cpm_fleet *fleet, const cp
     o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
     if (T > 1) {
         o.n_steps = T - 1; o.with_time = 0; o.rng.stream = 0;                               // main.jl:91-92
-        TRY(run_day_async(city, fleet, &o, nullptr));
+        TRY(run_day_async(city, fleet, &o, nullptr, false));
         // lost-car visits of the IVP survive the next day's reset of the scalar block (device-to-device, no host sync)
         CU(cudaMemcpyAsync(fleet->lost_acc.p, &fleet->scalars.as<Scalars>()->lost, sizeof(unsigned long long),
                            cudaMemcpyDeviceToDevice, ctx->st));

@@ -23,13 +23,13 @@ namespace cpm {
 constexpr int kCarQueue = 64;          // entries per warp queue (a batch is served as soon as 32 have queued up)
 constexpr uint16_t kNoCar = 0xFFFFu;   // slot beyond the CTA's last car
 
-template <int THREADS, bool INJ, bool TIME>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayArgs a)
+template <int THREADS, bool INJ, bool TIME, int U>
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(const DayArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned long long red[2];
+    __shared__ unsigned long long red[3];
     constexpr int WARPS = THREADS / 32;
-    constexpr int U = 4;                 // cars per lane and trip: four independent Philox chains
+    constexpr int E = 1;                 // queue entries per lane and batch (2 measured slower: larger partial batches, 64 registers)
     const int64_t N = a.N, C = a.C, NN = a.N * a.N;
     const int Ni = (int)N, NB = Ni + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -39,19 +39,20 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
     unsigned long long *const fq = reinterpret_cast<unsigned long long *>(smem_raw) + (WARPS + wid) * kCarQueue;
     double *const pd_s = reinterpret_cast<double *>(smem_raw) + (TIME ? 2 : 1) * WARPS * kCarQueue;
     uint32_t *const hnet = reinterpret_cast<uint32_t *>(pd_s + (a.pd_smem ? N : 0));
-    uint32_t *const hdrv = hnet + NB;
-    uint8_t *const rz_s = reinterpret_cast<uint8_t *>(hdrv + NB);
+    uint32_t *const hdrv = hnet + NB;                 // two 16-bit counters per word: a CTA holds fewer than 65,536 cars
+    const int NW = (NB + 1) >> 1;                     // words of hdrv
+    uint8_t *const rz_s = reinterpret_cast<uint8_t *>(hdrv + NW);
     uint16_t *const zs = reinterpret_cast<uint16_t *>(rz_s + ((N + 3) & ~(int64_t)3));
-    const int cpc = a.cars_per_cta, spw = cpc / WARPS;   // slots per CTA / per warp (spw: a multiple of 32 * U)
+    const int cpc = a.cars_per_cta, spw = cpc / WARPS;   // slots per CTA / per warp (spw: a multiple of 32)
     const int wbase = wid * spw;
-    unsigned long long t_hi = 0ull, t_lo = 0ull;
-    if (tid < 2) red[tid] = 0ull;
+    unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
+    if (tid < 3) red[tid] = 0ull;
 
     for (int64_t base = (int64_t)blockIdx.x * cpc; base < C; base += (int64_t)gridDim.x * cpc) {
         const int n_cars = (int)((C - base < cpc) ? (C - base) : cpc);
         const int64_t car0 = base + wbase;   // the warp's first car
         __syncthreads();
-        for (int x = tid; x < 2 * NB; x += THREADS) hnet[x] = 0u;   // hnet and hdrv are adjacent
+        for (int x = tid; x < NB + NW; x += THREADS) hnet[x] = 0u;   // hnet and hdrv are adjacent
         __syncthreads();
         // the CTA's cars: zones into shared memory, and their share of the occupancy at the first step
         for (int x = tid; x < cpc; x += THREADS) {
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
             if (x < n_cars) {
                 const int32_t z = a.zone[base + x];
                 z16 = (z >= 1 && z <= Ni) ? (uint16_t)z : (uint16_t)0;   // anything else is a lost car (documented extension)
-                if (a.cnt0) atomicAdd(&hnet[z16 ? z16 - 1 : Ni], 1u);
+                if (a.cnt0) atomicAdd(&hnet[z16 ? z16 - 1 : Ni], 1u);   // (null without counts)
             }
             zs[x] = z16;
         }
@@ -85,71 +86,121 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
 
             uint32_t dq_head = 0, fq_head = 0;
             int dq_cnt = 0, fq_cnt = 0;
-            auto far_batch = [&](int n) {   // travel times of up to 32 queued cars (src/resampling.jl:61-70), one per lane
-                if (lane < n) {
-                    const unsigned long long e = fq[(fq_head + lane) & (kCarQueue - 1)];
-                    const int64_t car = car0 + (int64_t)(e & 0xFFFull);
-                    const uint32_t odp = (uint32_t)(e >> 12);
-                    const int64_t od = (int64_t)(odp & 0xffffu) + N * (int64_t)(odp >> 16);
-                    double mean, sd;
-                    if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * hour); mean = ms.x; sd = ms.y; }
-                    else { mean = __ldg(a.dm + od + NN * hour); sd = __ldg(a.dm + od + NN * (hour + a.T_tab)); }
-                    double u3;
-                    if (INJ) u3 = a.rng.u_time[car + uoff];
-                    else { uint32_t o[4]; philox_words(a.rng, car, (uint32_t)s, 1u, o); u3 = u52(o[0], o[1]); }
-                    if (sd == 0.0) sd = 0.1 * mean;                                   // :65-67
-                    fx_add(t_hi, t_lo, truncnormal(mean, sd, u3));                    // :68
+            // travel times of up to 32 * E queued cars (src/resampling.jl:61-70), E per lane: the E table gathers of a lane
+            // are in flight together
+            auto far_batch = [&](int n) {
+                double mean[E], sd[E];
+                int64_t car[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    mean[e] = sd[e] = 0.0; car[e] = 0;
+                    if (lane + 32 * e < n) {
+                        const unsigned long long q = fq[(fq_head + lane + 32 * e) & (kCarQueue - 1)];
+                        car[e] = car0 + (int64_t)(q & 0xFFFull);
+                        const uint32_t odp = (uint32_t)(q >> 12);
+                        const int64_t od = (int64_t)(odp & 0xffffu) + N * (int64_t)(odp >> 16);
+                        if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * hour); mean[e] = ms.x; sd[e] = ms.y; }
+                        else { mean[e] = __ldg(a.dm + od + NN * hour); sd[e] = __ldg(a.dm + od + NN * (hour + a.T_tab)); }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (lane + 32 * e < n) {
+                        double u3;
+                        if (INJ) u3 = a.rng.u_time[car[e] + uoff];
+                        else { uint32_t o[4]; philox_words(a.rng, car[e], (uint32_t)s, 1u, o); u3 = u52(o[0], o[1]); }
+                        if (sd[e] == 0.0) sd[e] = 0.1 * mean[e];                      // :65-67
+                        fx_add(t_hi, t_lo, truncnormal(mean[e], sd[e], u3));          // :68
+                    }
                 }
             };
-            auto drive_batch = [&](int n) {   // categorical destinations of up to 32 queued drivers (src/resampling.jl:26-49)
-                bool far = false;
-                uint32_t slot = 0, odp = 0;
-                if (lane < n) {
-                    const unsigned long long e = dq[(dq_head + lane) & (kCarQueue - 1)];
-                    slot = (uint32_t)(e & 0xFFFull);
-                    const unsigned long long uq = e >> 12;   // the 52-bit integer of u_dest (Philox)
-                    const int z = (int)zs[wbase + slot];     // 1-based origin
-                    const double *__restrict__ row = cdf_t + (int64_t)(z - 1) * a.ldc;
-                    const uint16_t *__restrict__ gd = reinterpret_cast<const uint16_t *>(row + a.goff);
-                    const double u2 = INJ ? a.rng.u_dest[car0 + slot + uoff]
-                                          : __hiloint2double((int)((uint32_t)(uq >> 32) | 0x3FF00000u), (int)(uint32_t)uq) - 1.0;
-                    int32_t dest = 0;
-                    if (u2 > 0.0) {
-                        int32_t lo, hi;
-                        if (INJ && !(u2 < 1.0)) { lo = __ldg(gd + a.G); hi = Ni; }
-                        else {
-                            const uint32_t c = INJ ? (uint32_t)(u2 * (double)a.G) : (uint32_t)(uq >> (52 - (32 - a.gshift)));
-                            lo = __ldg(gd + c); hi = __ldg(gd + c + 1);
-                        }
-                        // first index in [lo, hi] whose CDF value is not below u2 (NaN counts as not below, like the binary
-                        // search of the other samplers: the row is non-decreasing with a NaN tail, so the predicate is
-                        // monotone and the answer is the same index).  The guide leaves a window of a few entries: four
-                        // independent loads per trip instead of a chain of dependent probes.
-                        const int32_t last = hi < Ni ? hi : Ni - 1;
-                        for (int32_t idx = lo; idx <= last; idx += 4) {
-                            double r[4];
+            // categorical destinations of up to 32 * E queued drivers (src/resampling.jl:26-49), E per lane, in phases so
+            // that the E guide lookups, then the E row windows, of a lane are in flight together
+            auto drive_batch = [&](int n) {
+                uint32_t slot[E];
+                int z[E];
+                int32_t lo[E], last[E], dest[E];
+                double u2[E];
+                const double *row[E];
+                bool act[E];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) r[q] = (idx + q <= last) ? __ldg(row + idx + q) : CUDART_INF;
+                for (int e = 0; e < E; ++e) {   // queue entry, origin, guide cell
+                    act[e] = lane + 32 * e < n;
+                    slot[e] = 0; z[e] = 1; lo[e] = 1; last[e] = 0; dest[e] = 0; u2[e] = 0.0; row[e] = cdf_t;
+                    if (act[e]) {
+                        const unsigned long long q = dq[(dq_head + lane + 32 * e) & (kCarQueue - 1)];
+                        slot[e] = (uint32_t)(q & 0xFFFull);
+                        const unsigned long long uq = q >> 12;   // the 52-bit integer of u_dest (Philox)
+                        z[e] = (int)zs[wbase + slot[e]];         // 1-based origin
+                        row[e] = cdf_t + (int64_t)(z[e] - 1) * a.ldc;
+                        const uint16_t *__restrict__ gd = reinterpret_cast<const uint16_t *>(row[e] + a.goff);
+                        u2[e] = INJ ? a.rng.u_dest[car0 + slot[e] + uoff]
+                                    : __hiloint2double((int)((uint32_t)(uq >> 32) | 0x3FF00000u), (int)(uint32_t)uq) - 1.0;
+                        if (u2[e] > 0.0) {
+                            int32_t hi;
+                            if (INJ && !(u2[e] < 1.0)) { lo[e] = __ldg(gd + a.G); hi = Ni; }
+                            else {
+                                const uint32_t c = INJ ? (uint32_t)(u2[e] * (double)a.G) : (uint32_t)(uq >> (52 - (32 - a.gshift)));
+                                lo[e] = __ldg(gd + c); hi = __ldg(gd + c + 1);
+                            }
+                            last[e] = hi < Ni ? hi : Ni - 1;
+                        }
+                    }
+                }
+                // first index in [lo, last] whose CDF value is not below u2 (NaN counts as not below, like the binary search
+                // of the other samplers: the row is non-decreasing with a NaN tail, so the predicate is monotone and the
+                // answer is the same index).  The guide leaves a window of a few entries: four independent loads per trip
+                // and entry instead of a chain of dependent probes.
+                bool more;
+                do {
+                    double r[E][4];
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) r[e][q] = (lo[e] + q <= last[e]) ? __ldg(row[e] + lo[e] + q) : CUDART_INF;
+                    more = false;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if (lo[e] <= last[e]) {
                             int q = 4;
                             double v = 0.0;
 #pragma unroll
-                            for (int k = 3; k >= 0; --k) if (!(r[k] < u2)) { q = k; v = r[k]; }
-                            if (q < 4) { if (idx + q <= last && u2 <= v) dest = idx + q + 1; break; }   // else 0: lost (:32,40)
+                            for (int k = 3; k >= 0; --k) if (!(r[e][k] < u2[e])) { q = k; v = r[e][k]; }
+                            if (q < 4) {
+                                if (lo[e] + q <= last[e] && u2[e] <= v) dest[e] = lo[e] + q + 1;   // else 0: lost (:32,40)
+                                lo[e] = last[e] + 1;   // done
+                            } else {
+                                lo[e] += 4;
+                                more |= lo[e] <= last[e];
+                            }
                         }
                     }
-                    if (dest != z) {
-                        zs[wbase + slot] = (uint16_t)dest;                            // :81-83
-                        atomicSub(&hnet[z - 1], 1u);
-                        atomicAdd(&hnet[dest >= 1 ? dest - 1 : Ni], 1u);
-                        if (TIME && dest >= 1) { far = true; odp = (uint32_t)(z - 1) | ((uint32_t)(dest - 1) << 16); }
-                    } else if (TIME) t_hi += 300ull;                                  // :58-59
+                } while (__any_sync(0xffffffffu, more));
+                bool far[E];
+                uint32_t odp[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    far[e] = false; odp[e] = 0;
+                    if (act[e]) {
+                        if (dest[e] != z[e]) {
+                            zs[wbase + slot[e]] = (uint16_t)dest[e];                      // :81-83
+                            if (a.counts) {
+                                atomicSub(&hnet[z[e] - 1], 1u);
+                                atomicAdd(&hnet[dest[e] >= 1 ? dest[e] - 1 : Ni], 1u);
+                            }
+                            if (TIME && dest[e] >= 1) { far[e] = true; odp[e] = (uint32_t)(z[e] - 1) | ((uint32_t)(dest[e] - 1) << 16); }
+                        } else if (TIME) t_hi += 300ull;                                  // :58-59
+                    }
                 }
                 if (TIME) {
-                    const uint32_t m_far = __ballot_sync(0xffffffffu, far);
-                    if (far) fq[(fq_head + fq_cnt + __popc(m_far & lt_mask)) & (kCarQueue - 1)] = ((unsigned long long)odp << 12) | slot;
-                    fq_cnt += __popc(m_far);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const uint32_t m_far = __ballot_sync(0xffffffffu, far[e]);
+                        if (far[e]) fq[(fq_head + fq_cnt + __popc(m_far & lt_mask)) & (kCarQueue - 1)] = ((unsigned long long)odp[e] << 12) | slot[e];
+                        fq_cnt += __popc(m_far);
+                    }
                     __syncwarp();
-                    if (fq_cnt >= 32) { far_batch(32); fq_head += 32; fq_cnt -= 32; __syncwarp(); }
+                    if (fq_cnt >= 32 * E) { far_batch(32 * E); fq_head += 32 * E; fq_cnt -= 32 * E; __syncwarp(); }
                 }
             };
 
@@ -157,10 +208,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
                 uint16_t z[U];
                 double pdz[U];
 #pragma unroll
-                for (int j = 0; j < U; ++j) z[j] = zs[wbase + k0 + j * 32 + lane];
+                for (int j = 0; j < U; ++j) z[j] = (k0 + j * 32 < spw) ? zs[wbase + k0 + j * 32 + lane] : kNoCar;
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
                     const bool parked = z[j] != 0 && z[j] != kNoCar;
+                    if (!a.counts) lost += z[j] == 0;   // without the per-step rows the lost-car visits are counted here
                     pdz[j] = !parked ? -1.0 : (a.pd_smem ? pd_s[z[j] - 1] : __ldg(pd_t + (z[j] - 1)));   // -1: never drives
                 }
                 bool srch[U];
@@ -179,11 +231,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
                     }
                     srch[j] = false;
                     if (drive) {
-                        atomicAdd(&hdrv[z[j] - 1], 1u);                               // src/saveresults.jl:13-15
+                        if (a.counts) atomicAdd(&hdrv[(z[j] - 1) >> 1], 1u << (((z[j] - 1) & 1) * 16));   // src/saveresults.jl:13-15
                         if (rz_s[z[j] - 1]) { if (TIME) t_hi += 300ull; }             // all-zero row: stays, 5 min (:35-36, :58-59)
                         else {
                             srch[j] = true;
-                            if (!INJ) {   // the guide cell is needed once 32 drivers have queued up: start it towards L2 now
+                            if (!INJ && a.prefetch) {   // the guide cell is needed once a batch has queued up: start it towards L2 now
                                 const uint16_t *gd = reinterpret_cast<const uint16_t *>(cdf_t + (int64_t)(z[j] - 1) * a.ldc + a.goff);
                                 asm volatile("prefetch.global.L2 [%0];" ::"l"(gd + (uint32_t)(uq[j] >> (52 - (32 - a.gshift)))));
                             }
@@ -196,19 +248,26 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
                     if (srch[j]) dq[(dq_head + dq_cnt + __popc(m & lt_mask)) & (kCarQueue - 1)] = (uq[j] << 12) | (uint32_t)(k0 + j * 32 + lane);
                     dq_cnt += __popc(m);
                     __syncwarp();
-                    if (dq_cnt >= 32) { drive_batch(32); dq_head += 32; dq_cnt -= 32; __syncwarp(); }
+                    if (dq_cnt >= 32 * E) { drive_batch(32 * E); dq_head += 32 * E; dq_cnt -= 32 * E; __syncwarp(); }
                 }
             }
             if (dq_cnt > 0) { drive_batch(dq_cnt); __syncwarp(); }
-            if (TIME && fq_cnt > 0) far_batch(fq_cnt);
+            if (TIME) while (fq_cnt > 0) { const int n = fq_cnt < 32 * E ? fq_cnt : 32 * E; far_batch(n); fq_head += n; fq_cnt -= n; }
 
-            __syncthreads();
-            // this step's rows: one reduction per non-empty bin
-            uint32_t *const net_s = a.net + (size_t)s * NB, *const drv_s = a.drv + (size_t)s * NB;
-            for (int x = tid; x < NB; x += THREADS) {
-                const uint32_t v = hnet[x], d = hdrv[x];
-                if (v) { atomicAdd(net_s + x, v); hnet[x] = 0u; }
-                if (d) { atomicAdd(drv_s + x, d); hdrv[x] = 0u; }
+            if (a.counts) {
+                __syncthreads();
+                // this step's rows: one reduction per non-empty bin
+                uint32_t *const net_s = a.net + (size_t)s * NB, *const drv_s = a.drv + (size_t)s * NB;
+                for (int x = tid; x < NB; x += THREADS) {
+                    const uint32_t v = hnet[x];
+                    if (v) { atomicAdd(net_s + x, v); hnet[x] = 0u; }
+                }
+                for (int x = tid; x < NW; x += THREADS) {
+                    const uint32_t d = hdrv[x];
+                    if (d & 0xffffu) atomicAdd(drv_s + 2 * x, d & 0xffffu);
+                    if (d >> 16) atomicAdd(drv_s + 2 * x + 1, d >> 16);
+                    if (d) hdrv[x] = 0u;
+                }
             }
         }
         __syncthreads();
@@ -218,15 +277,20 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_day_cars(const DayA
     // totals: integer block reduction, a few global atomics per CTA
     __syncthreads();
     t_hi = warp_sum_u64(t_hi); t_lo = warp_sum_u64(t_lo);
+    if (!a.counts) lost = warp_sum_u64(lost);
     if (lane == 0) {
         if (t_hi) atomicAdd(&red[0], t_hi);
         if (t_lo) atomicAdd(&red[1], t_lo);
+        if (lost) atomicAdd(&red[2], lost);
     }
     __syncthreads();
-    if (TIME && tid == 0) {
-        const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
-        if (hi) atomicAdd(a.t_hi, hi);
-        if (lo32) atomicAdd(a.t_lo, lo32);
+    if (tid == 0) {
+        if (TIME) {
+            const unsigned long long hi = red[0] + (red[1] >> 32), lo32 = red[1] & 0xffffffffull;
+            if (hi) atomicAdd(a.t_hi, hi);
+            if (lo32) atomicAdd(a.t_lo, lo32);
+        }
+        if (!a.counts && red[2]) atomicAdd(a.lost_visits, red[2]);
     }
 }
 
@@ -264,20 +328,21 @@ bool cars_geometry(int64_t N, int64_t C, int with_time, CarsGeom *g)
     if (N < 1 || N + 1 > 65535 || C < 1) return false;
     static const int threads_env = cars_env("CPM_CARS_THREADS", 1024);
     const int threads = threads_env == 512 ? 512 : 1024;
-    const int per_sm = 1024 / threads, warps = threads / 32;
+    const int per_sm = threads == 1024 ? 1 : 2, warps = threads / 32;
     const size_t cap = (size_t)(232448 - 1024 * per_sm) / per_sm - 64;   // opt-in maximum per SM minus the per-CTA reserve
     const size_t queues = (size_t)warps * kCarQueue * 8 * (with_time ? 2 : 1);
-    const size_t hist = 2 * (size_t)(N + 1) * 4 + (size_t)((N + 3) & ~(int64_t)3);
+    const size_t hist = (size_t)(N + 1) * 4 + (size_t)((N + 2) / 2) * 4 + (size_t)((N + 3) & ~(int64_t)3);   // hnet, hdrv (16-bit), rowzero
     const int64_t n_ctas = (int64_t)kSMs * per_sm;
-    const int64_t want = ((C + n_ctas - 1) / n_ctas + threads * 4 - 1) / ((int64_t)threads * 4) * ((int64_t)threads * 4);
+    const int64_t want = ((C + n_ctas - 1) / n_ctas + threads - 1) / threads * threads;   // every warp owns a multiple of 32 slots
     for (int pd_smem = 1; pd_smem >= 0; --pd_smem) {
         const size_t fixed = queues + hist + (pd_smem ? (size_t)N * 8 : 0) + 32;
-        if (fixed + (size_t)threads * 4 * 2 > cap) continue;
+        if (fixed + (size_t)threads * 2 > cap) continue;
         int64_t cpc = (int64_t)((cap - fixed) / 2);
-        cpc = cpc / (threads * 4) * (threads * 4);            // every warp owns a multiple of 32 * 4 slots
+        cpc = cpc / threads * threads;
         if (cpc > want) cpc = want;
         if (cpc > (int64_t)4096 * warps) cpc = (int64_t)4096 * warps;   // 12-bit slot numbers inside a warp
-        if (cpc < threads * 4) continue;
+        if (cpc > 65535 / threads * threads) cpc = 65535 / threads * threads;   // 16-bit driver counters per CTA and bin
+        if (cpc < threads) continue;
         g->threads = threads; g->pd_smem = pd_smem; g->cars_per_cta = (int)cpc;
         const int64_t need = (C + cpc - 1) / cpc;
         g->n_ctas = (int)(need < n_ctas ? need : n_ctas);
@@ -287,8 +352,8 @@ bool cars_geometry(int64_t N, int64_t C, int with_time, CarsGeom *g)
     return false;
 }
 
-template <int THREADS, bool INJ, bool TIME>
-static int day_cars_launch(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
+template <int THREADS, bool INJ, bool TIME, int U>
+static int day_cars_launch_u(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
 {
     // the opt-in applies to the current device's copy of the kernel: once per (device, instantiation)
     static std::mutex mu;
@@ -299,23 +364,35 @@ static int day_cars_launch(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
         std::lock_guard<std::mutex> lk(mu);
         size_t &have = granted[dev];
         if (g.smem > have) {
-            if (cudaFuncSetAttribute(k_day_cars<THREADS, INJ, TIME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(k_day_cars<THREADS, INJ, TIME, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) != cudaSuccess) return -1;
             have = g.smem;
         }
     }
-    k_day_cars<THREADS, INJ, TIME><<<(unsigned)g.n_ctas, THREADS, g.smem, st>>>(a);
+    k_day_cars<THREADS, INJ, TIME, U><<<(unsigned)g.n_ctas, THREADS, g.smem, st>>>(a);
     return 1;
+}
+
+template <int THREADS, bool INJ, bool TIME>
+static int day_cars_launch(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
+{
+    // cars per lane and trip (independent Philox chains): 2 by default, CPM_CARS_U = 1 / 4 for the other shapes
+    static const int u = cars_env("CPM_CARS_U", 2);
+    if (u == 1) return day_cars_launch_u<THREADS, INJ, TIME, 1>(a, g, st);
+    return u == 4 ? day_cars_launch_u<THREADS, INJ, TIME, 4>(a, g, st) : day_cars_launch_u<THREADS, INJ, TIME, 2>(a, g, st);
+}
+
+template <int THREADS>
+static int day_cars_launch_t(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
+{
+    const bool inj = a.rng.mode == 1, time = a.with_time != 0;
+    if (inj) return time ? day_cars_launch<THREADS, true, true>(a, g, st) : day_cars_launch<THREADS, true, false>(a, g, st);
+    return time ? day_cars_launch<THREADS, false, true>(a, g, st) : day_cars_launch<THREADS, false, false>(a, g, st);
 }
 
 int launch_day_cars(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
 {
-    const bool inj = a.rng.mode == 1, time = a.with_time != 0;
-    if (g.threads == 512) {
-        if (inj) return time ? day_cars_launch<512, true, true>(a, g, st) : day_cars_launch<512, true, false>(a, g, st);
-        return time ? day_cars_launch<512, false, true>(a, g, st) : day_cars_launch<512, false, false>(a, g, st);
-    }
-    if (inj) return time ? day_cars_launch<1024, true, true>(a, g, st) : day_cars_launch<1024, true, false>(a, g, st);
-    return time ? day_cars_launch<1024, false, true>(a, g, st) : day_cars_launch<1024, false, false>(a, g, st);
+    if (g.threads == 512) return day_cars_launch_t<512>(a, g, st);
+    return day_cars_launch_t<1024>(a, g, st);
 }
 
 int launch_cars_export_counts(const uint32_t *cnt0, const uint32_t *net, const uint32_t *drv, int N, int64_t n_steps,

@@ -66,7 +66,7 @@ int launch_reduce_partials(const double *partials, int n, double *out, cudaStrea
 // the car-resident day kernel: one launch = steps [step0, step0 + n_steps) of a day for all cars
 struct CarsGeom {
     int n_ctas, threads;
-    int cars_per_cta;          // car slots a CTA keeps in shared memory (a multiple of 4 * threads)
+    int cars_per_cta;          // car slots a CTA keeps in shared memory (a multiple of threads)
     int pd_smem;               // the hour's p_drive column is staged in shared memory
     size_t smem;
 };
@@ -75,11 +75,13 @@ struct DayArgs {
     const double2 *msd;        // nullable: (mean, std) pairs
     int64_t N, T_tab, C;
     int64_t step0, n_steps, steps_per_hour;
-    int32_t with_time, pd_smem, cars_per_cta;
+    int32_t with_time, pd_smem, cars_per_cta, prefetch;
+    int32_t counts;            // 0: no per-zone counts (cnt0 / net / drv unused); the lost-car visits go to lost_visits
     int32_t *zone;             // [C] in/out: 1-based zone, 0 = lost
     uint32_t *cnt0;            // nullable: [N+1] += occupancy of every bin before step0 (bin N = lost cars)
     uint32_t *net;             // [day steps][N+1] += net arrivals per bin and step (two's complement)
     uint32_t *drv;             // [day steps][N+1] += driving cars per origin and step
+    unsigned long long *lost_visits;   // counts == 0 only: += cars in zone 0, summed over the steps
     RngDev rng;
     unsigned long long *t_hi, *t_lo;
 };

@@ -11,8 +11,8 @@ IFS=';' read -ra VS <<< "${VARIANTS:-U=2 T=1024 R=0}"
 for v in "${VS[@]}"; do
   eval $v
   f=$out/bench_U${U}_T${T}_R${R}
-  f=${f}_E${E:-0}_I${I:-1024}_UT${UT:-2}_B${B:-0}_CT${CT:-1024}
-  CPM_PREFER_BUCKET=${B:-0} CPM_CARS_THREADS=${CT:-1024} CPM_BUCKET_U_TIME=${UT:-2} CPM_BUCKET_IVP_THREADS=${I:-1024} CPM_GATHER_EVICT_FIRST=${E:-0} CPM_BUCKET_U=$U CPM_BUCKET_THREADS=$T CPM_BUCKET_RING=$R timeout 300 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline ${BENCH_FLAGS:---no-multi --no-rows --pageable-steps 1 --e2e-steps 2} > $f.json 2> $f.err
+  f=${f}_E${E:-0}_I${I:-1024}_UT${UT:-2}_B${B:-0}_CT${CT:-1024}_CU${CU:-4}_PF${PF:-0}
+  CPM_PREFER_BUCKET=${B:-0} CPM_CARS_THREADS=${CT:-1024} CPM_CARS_U=${CU:-4} CPM_CARS_PREFETCH=${PF:-0} CPM_BUCKET_U_TIME=${UT:-2} CPM_BUCKET_IVP_THREADS=${I:-1024} CPM_GATHER_EVICT_FIRST=${E:-0} CPM_BUCKET_U=$U CPM_BUCKET_THREADS=$T CPM_BUCKET_RING=$R timeout 300 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline ${BENCH_FLAGS:---no-multi --no-rows --pageable-steps 1 --e2e-steps 2} > $f.json 2> $f.err
   python - "$f.json" "$v" <<'PY'
 import json, sys
 try:
