@@ -41,21 +41,23 @@ WORKLOADS = {
 }
 PARAMS = dict(e_drive=0.5, e_dest=2, p_min=0.1, p_max=0.9)   # main.jl:37-40
 REF_WALL_S = 150.0   # wall-clock target of a whole `--impl reference` run
-# dram__bytes_read.sum + dram__bytes_write.sum per k_bucket_sample launch: written by profiles/summarize_metrics.py from an
-# ncu capture of THIS kernel source (the file records the sha256 of csrc/bucket.cu it was taken with)
+# dram__bytes_read.sum + dram__bytes_write.sum of the step kernel per HMM step: written by profiles/make_ncu_traffic.py from an
+# ncu capture of THAT kernel source (the file records the kernel and the sha256 of its source file)
 NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
-def ncu_traffic(workload):
-    """(bytes per launch or None, note): the committed ncu DRAM traffic of the sampling kernel, only if it was captured
-    with the kernel source that is being timed now."""
+def ncu_traffic(workload, kernel):
+    """(bytes per step or None, note): the committed ncu DRAM traffic of the step kernel, only if it was captured from
+    the kernel that was timed and with the source that is being timed now."""
     import hashlib
     try:
         rec = json.load(open(NCU_TRAFFIC_FILE))[workload]
-        sha = hashlib.sha256(open(os.path.join(ROOT, "carparkingmaps_b200", "csrc", "bucket.cu"), "rb").read()).hexdigest()
-        if rec.get("bucket_cu_sha256") != sha:
-            return None, "no ncu capture of the current csrc/bucket.cu (profiles/ncu_traffic.json is from an older kernel)"
-        return float(rec["dram_bytes_per_launch"]), rec.get("source", "")
+        if rec.get("kernel") != kernel:
+            return None, f"the ncu capture on file is of {rec.get('kernel')}, the timed kernel is {kernel}"
+        sha = hashlib.sha256(open(os.path.join(ROOT, "carparkingmaps_b200", "csrc", rec["source_file"]), "rb").read()).hexdigest()
+        if rec.get("source_sha256") != sha:
+            return None, f"no ncu capture of the current csrc/{rec['source_file']} (profiles/ncu_traffic.json is from an older kernel)"
+        return float(rec["dram_bytes_per_step"]), rec.get("source", "")
     except Exception as e:
         return None, f"no ncu capture on file ({type(e).__name__})"
 
@@ -637,10 +639,16 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = measured_peak()
         B = alg_bytes_per_transition(N, cpz)
-        # the step kernel processes C transitions per launch
-        avg_launch_ms = step_ms / max(1, step_launches)
-        achieved = B * C_ / (avg_launch_ms * 1e-3) / 1e9
-        traffic, traffic_note = ncu_traffic(args.workload)
+        # the step kernel: k_day_cars runs a whole day per launch (two launches per pass: the IVP's T-1 steps and the
+        # resampling day's T steps, every launch bracketed with CUDA events), k_bucket_sample one step per launch (every
+        # third launch bracketed).  profile_end() returns the bracketed device time and the HMM steps it covers.
+        steps_timed = max(1, step_launches)
+        launches_timed = 2 * args.steps if step_kernel == "k_day_cars" else steps_timed
+        steps_per_launch = steps_timed / launches_timed
+        avg_launch_ms = step_ms / launches_timed
+        ms_per_hmm_step = step_ms / steps_timed
+        achieved = B * C_ * steps_per_launch / (avg_launch_ms * 1e-3) / 1e9
+        traffic, traffic_note = ncu_traffic(args.workload, step_kernel)
         h2d, d2h = (n_dm + n_dist) * 8, (N * T + T) * 8 + 16
         line = {
             "metric": "sampled car-transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
@@ -657,16 +665,16 @@ def run_own(args, N, cpz, T, rank, world, local_rank):
             "e2e_rows": e2e_rows,
             "gpu_launches": int(launches),
             "clocks": clk,
-            # dominant kernel: k_bucket_sample (one launch = one HMM step over all C cars).  Every third launch is bracketed
-            # with CUDA events on the library's stream inside the timed region; `traffic` is the ncu dram__bytes_read+write
-            # per launch of a committed capture of the SAME kernel source, or null (not a live figure).
-            "roofline": {"bound": "hbm", "kernel": step_kernel + (" (one launch runs all steps of a day; figures are per step)" if step_kernel == "k_day_cars" else " (per-step sampling kernel)"),
-                         "achieved": achieved,
+            # dominant kernel = the step kernel (k_day_cars: one launch = every step of a day over all C cars), timed with CUDA
+            # events on the library's stream inside the timed region; `traffic` is the ncu dram__bytes_read+write per launch of a
+            # committed capture of the SAME kernel source, or null (not a live figure).
+            "roofline": {"bound": "hbm", "kernel": step_kernel, "achieved": achieved,
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_note": traffic_note,
-                         "bytes_per_transition": B, "transitions_per_launch": C_, "avg_launch_ms": avg_launch_ms,
-                         "launches_timed": int(step_launches),
-                         "kernel_share_of_step": avg_launch_ms * (2 * T - 1) / (ms / args.steps)},
+                         "traffic": None if traffic is None else traffic * steps_per_launch, "traffic_note": traffic_note,
+                         "bytes_per_transition": B, "transitions_per_launch": C_ * steps_per_launch, "avg_launch_ms": avg_launch_ms,
+                         "launches_timed": int(launches_timed), "hmm_steps_per_launch": steps_per_launch,
+                         "ms_per_hmm_step": ms_per_hmm_step,
+                         "kernel_share_of_step": ms_per_hmm_step * (2 * T - 1) / (ms / args.steps)},
             "result_check": {"A_drive": A_drive, "lost": int(lost), "parking_sum_t1": float(parking[:, 0].sum()),
                              "parity_vs_oracle": parity},
             "multi_gpu": multi,

@@ -906,7 +906,6 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, boo
     a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
     a.N = N; a.T_tab = city->T; a.C = C; a.steps_per_hour = o->steps_per_hour; a.with_time = o->with_time;
     a.pd_smem = g.pd_smem; a.cars_per_cta = g.cars_per_cta;
-    { static const int pf = getenv("CPM_CARS_PREFETCH") ? atoi(getenv("CPM_CARS_PREFETCH")) : 0; a.prefetch = pf; }
     a.zone = f->zone.as<int32_t>();
     a.counts = want_counts ? 1 : 0;
     if (want_counts) { a.cnt0 = f->cars_cnt.as<uint32_t>(); a.net = a.cnt0 + NB; a.drv = a.net + (size_t)S * NB; }

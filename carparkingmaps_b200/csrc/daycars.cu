@@ -13,7 +13,6 @@
 // per non-empty bin into that step's global row; occupancy at step s+1 = occupancy at step s + net arrivals (export).
 // Same draws as every other sampler => identical results (tests compare with the oracle and with the bucket sampler).
 #include <math_constants.h>
-#include <cstdlib>
 #include <map>
 #include <mutex>
 #include "kernels.h"
@@ -22,6 +21,7 @@ namespace cpm {
 
 constexpr int kCarQueue = 64;          // entries per warp queue (a batch is served as soon as 32 have queued up)
 constexpr uint16_t kNoCar = 0xFFFFu;   // slot beyond the CTA's last car
+constexpr int kCarThreads = 1024;      // one CTA per SM
 
 template <int THREADS, bool INJ, bool TIME, int U>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(const DayArgs a)
@@ -233,13 +233,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                     if (drive) {
                         if (a.counts) atomicAdd(&hdrv[(z[j] - 1) >> 1], 1u << (((z[j] - 1) & 1) * 16));   // src/saveresults.jl:13-15
                         if (rz_s[z[j] - 1]) { if (TIME) t_hi += 300ull; }             // all-zero row: stays, 5 min (:35-36, :58-59)
-                        else {
-                            srch[j] = true;
-                            if (!INJ && a.prefetch) {   // the guide cell is needed once a batch has queued up: start it towards L2 now
-                                const uint16_t *gd = reinterpret_cast<const uint16_t *>(cdf_t + (int64_t)(z[j] - 1) * a.ldc + a.goff);
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(gd + (uint32_t)(uq[j] >> (52 - (32 - a.gshift)))));
-                            }
-                        }
+                        else srch[j] = true;
                     }
                 }
 #pragma unroll
@@ -317,18 +311,10 @@ __global__ void __launch_bounds__(256) k_cars_export_counts(const uint32_t *__re
 // ------------------------------------------------------------------------------------------------
 // geometry and launchers
 // ------------------------------------------------------------------------------------------------
-static int cars_env(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
 bool cars_geometry(int64_t N, int64_t C, int with_time, CarsGeom *g)
 {
     if (N < 1 || N + 1 > 65535 || C < 1) return false;
-    static const int threads_env = cars_env("CPM_CARS_THREADS", 1024);
-    const int threads = threads_env == 512 ? 512 : 1024;
-    const int per_sm = threads == 1024 ? 1 : 2, warps = threads / 32;
+    const int threads = kCarThreads, per_sm = 1, warps = threads / 32;
     const size_t cap = (size_t)(232448 - 1024 * per_sm) / per_sm - 64;   // opt-in maximum per SM minus the per-CTA reserve
     const size_t queues = (size_t)warps * kCarQueue * 8 * (with_time ? 2 : 1);
     const size_t hist = (size_t)(N + 1) * 4 + (size_t)((N + 2) / 2) * 4 + (size_t)((N + 3) & ~(int64_t)3);   // hnet, hdrv (16-bit), rowzero
@@ -372,27 +358,14 @@ static int day_cars_launch_u(const DayArgs &a, const CarsGeom &g, cudaStream_t s
     return 1;
 }
 
-template <int THREADS, bool INJ, bool TIME>
-static int day_cars_launch(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
-{
-    // cars per lane and trip (independent Philox chains): 2 by default, CPM_CARS_U = 1 / 4 for the other shapes
-    static const int u = cars_env("CPM_CARS_U", 2);
-    if (u == 1) return day_cars_launch_u<THREADS, INJ, TIME, 1>(a, g, st);
-    return u == 4 ? day_cars_launch_u<THREADS, INJ, TIME, 4>(a, g, st) : day_cars_launch_u<THREADS, INJ, TIME, 2>(a, g, st);
-}
-
-template <int THREADS>
-static int day_cars_launch_t(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
-{
-    const bool inj = a.rng.mode == 1, time = a.with_time != 0;
-    if (inj) return time ? day_cars_launch<THREADS, true, true>(a, g, st) : day_cars_launch<THREADS, true, false>(a, g, st);
-    return time ? day_cars_launch<THREADS, false, true>(a, g, st) : day_cars_launch<THREADS, false, false>(a, g, st);
-}
-
 int launch_day_cars(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
 {
-    if (g.threads == 512) return day_cars_launch_t<512>(a, g, st);
-    return day_cars_launch_t<1024>(a, g, st);
+    // one CTA of 1,024 threads per SM, two cars per lane and trip.  Measured at cfg2 (profiles/README.md): 2 x 512 and
+    // 2 x 768 threads per SM 45 % / 95 % slower per step, four cars per lane 11 % slower, one car per lane 2 % slower.
+    constexpr int T = kCarThreads, U = 2;
+    const bool inj = a.rng.mode == 1, time = a.with_time != 0;
+    if (inj) return time ? day_cars_launch_u<T, true, true, U>(a, g, st) : day_cars_launch_u<T, true, false, U>(a, g, st);
+    return time ? day_cars_launch_u<T, false, true, U>(a, g, st) : day_cars_launch_u<T, false, false, U>(a, g, st);
 }
 
 int launch_cars_export_counts(const uint32_t *cnt0, const uint32_t *net, const uint32_t *drv, int N, int64_t n_steps,
