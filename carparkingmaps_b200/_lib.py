@@ -108,6 +108,7 @@ SIGNATURES = {
                                 C.POINTER(_d), C.POINTER(_i64), C.POINTER(_i64)]),
     "cpm_sweep": (_i32, [_vp, _vp, _i64, C.POINTER(CParams), _i64, _u64, _vp, _vp, _vp, _vp]),
     "cpm_debug_bucket_geometry": (_i32, [_i64, _i64, _i32, _vp]),
+    "cpm_debug_cars_geometry": (_i32, [_i64, _i64, _i32, C.POINTER(_i64)]),
     "cpm_sample_datasets_multi": (_i32, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, C.POINTER(CParams), _i64, _u64, _vp, _vp, _vp, _vp]),
     "cpm_split_city_multi": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp, C.POINTER(CParams), _i64, _i64, _i64, _i32, _u64, C.c_uint32,
                              _vp, _vp, C.POINTER(_d), C.POINTER(_i64), C.POINTER(_d)]),

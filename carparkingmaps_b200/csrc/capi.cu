@@ -505,6 +505,19 @@ extern "C" int32_t cpm_debug_bucket_geometry(int64_t N, int64_t C, int32_t with_
     return CPM_OK;
 }
 
+// The same for the car-resident day kernel (csrc/daycars.cu): out6 = {supported, CTAs, threads, car slots per CTA,
+// p_drive column staged in shared memory, bytes of shared memory}.
+extern "C" int32_t cpm_debug_cars_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out6)
+{
+    ARG(out6 && N >= 1 && C >= 1);
+    CarsGeom g;
+    memset(&g, 0, sizeof g);
+    const bool ok = cars_geometry(N, C, with_time, &g);
+    const int64_t v[6] = { ok ? 1 : 0, g.n_ctas, g.threads, g.cars_per_cta, g.pd_smem, (int64_t)g.smem };
+    for (int k = 0; k < 6; ++k) out6[k] = v[k];
+    return CPM_OK;
+}
+
 static int32_t city_alloc_cdf(cpm_city *c)
 {
     cdf_layout(c->N, &c->goff, &c->G, &c->ldc);

@@ -61,3 +61,51 @@ def test_any_fleet_size(N, cars, with_time):
 def test_too_many_zones_fall_back():
     assert not geom(30000, 30000 * 10, 1)["supported"]
     assert not geom(70000, 70000, 0)["supported"]
+
+
+# ---- the car-resident day kernel (csrc/daycars.cu cars_geometry) ------------------------------------------------------
+def cars_geom(N, cars, with_time):
+    out = (C.c_int64 * 6)()
+    L.check(L.lib().cpm_debug_cars_geometry(int(N), int(cars), int(with_time), out))
+    return dict(zip(("supported", "n_ctas", "threads", "cars_per_cta", "pd_smem", "smem"), list(out)))
+
+
+def check_cars(N, cars, with_time):
+    g = cars_geom(N, cars, with_time)
+    if not g["supported"]:
+        assert N > 25000, (N, cars, g)            # 7 bytes of per-zone tables per zone + queues + 1,024 cars must fit 227 KB
+        return g
+    assert g["threads"] == 1024 and 1 <= g["n_ctas"] <= 148
+    cpc = g["cars_per_cta"]
+    assert cpc % g["threads"] == 0 and cpc >= g["threads"]
+    assert cpc // 32 <= 4096                      # 12-bit slot numbers inside a warp
+    assert cpc <= 65535                           # 16-bit driver counters per CTA and bin
+    assert g["smem"] <= SMEM_CAP - 1024
+    tables = (N + 1) * 4 + (N + 2) // 2 * 4 + N + (8 * N if g["pd_smem"] else 0)
+    assert g["smem"] >= tables + 2 * cpc + 32 * 64 * 8 * (2 if with_time else 1)
+    # every car is covered: a CTA walks blocks of cars_per_cta cars with stride n_ctas
+    assert g["n_ctas"] * cpc >= cars or g["n_ctas"] == 148
+    if g["n_ctas"] < 148:
+        assert (g["n_ctas"] - 1) * cpc < cars     # no idle CTA
+    return g
+
+
+@pytest.mark.parametrize("N,cpz", [(100, 1000), (2400, 1000), (500, 1000), (4000, 1000), (10000, 1250), (6, 1), (1, 7), (2400, 8)])
+def test_cars_named_configs(N, cpz):
+    for wt in (0, 1):
+        assert check_cars(N, N * cpz, wt)["supported"]
+    if (N, cpz) == (2400, 1000):
+        g = cars_geom(N, N * cpz, 1)
+        assert g["cars_per_cta"] == 16384 and g["n_ctas"] == 147 and g["pd_smem"] == 1
+
+
+@settings(max_examples=300, deadline=None)
+@given(st.integers(1, 30000), st.integers(1, 3000), st.booleans())
+def test_cars_any_city_size(N, cpz, with_time):
+    check_cars(N, N * cpz, with_time)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.integers(1, 5000), st.integers(1, 2**31 - 1), st.booleans())
+def test_cars_any_fleet_size(N, cars, with_time):
+    check_cars(N, cars, with_time)
