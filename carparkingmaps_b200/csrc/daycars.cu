@@ -7,7 +7,7 @@
 // kernel boundary between steps.  Per step a warp
 //   1. decides for each of its cars whether it drives (one Philox block, the hour's p_drive column from shared memory),
 //   2. queues the drivers and serves them in dense batches of 32: guide cell -> a window of a few CDF entries of the
-//      origin's row (global memory; the hour's rows are L2-resident for cities up to Melbourne size) -> destination,
+//      origin's row (global memory) -> destination,
 //   3. queues the cars that changed zone and draws their travel times in dense batches (resampling day only).
 // Counts: per-CTA shared-memory histograms (net arrivals and drivers per zone), flushed once per step with one reduction
 // per non-empty bin into that step's global row; occupancy at step s+1 = occupancy at step s + net arrivals (export).
@@ -22,6 +22,7 @@ namespace cpm {
 constexpr int kCarQueue = 64;          // entries per warp queue (a batch is served as soon as 32 have queued up)
 constexpr uint16_t kNoCar = 0xFFFFu;   // slot beyond the CTA's last car
 constexpr int kCarThreads = 1024;      // one CTA per SM
+constexpr int kWindow = 8;             // CDF entries per window trip (4: +2 % per step, one more trip for half of the batches)
 
 template <int THREADS, bool INJ, bool TIME, int U>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(const DayArgs a)
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long red[3];
     constexpr int WARPS = THREADS / 32;
+    constexpr int W = kWindow;
     constexpr int E = 1;                 // queue entries per lane and batch (2 measured slower: larger partial batches, 64 registers)
     const int64_t N = a.N, C = a.C, NN = a.N * a.N;
     const int Ni = (int)N, NB = Ni + 1;
@@ -45,6 +47,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
     uint16_t *const zs = reinterpret_cast<uint16_t *>(rz_s + ((N + 3) & ~(int64_t)3));
     const int cpc = a.cars_per_cta, spw = cpc / WARPS;   // slots per CTA / per warp (spw: a multiple of 32)
     const int wbase = wid * spw;
+    // With per-step rows the warps of a CTA meet at every step anyway, so the hour's p_drive / rowzero columns are staged in
+    // shared memory; without (the IVP of a dataset pass) the warps run through the day without a single block barrier and
+    // read the two columns through L1.
+    const bool staged = a.counts != 0;   // (staging without rows: +2 % per step at cfg2)
     unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
     if (tid < 3) red[tid] = 0ull;
 
@@ -77,12 +83,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
             const double *__restrict__ pd_t = a.p_drive + N * hour;
             const double *__restrict__ cdf_t = a.cdf + hour * N * a.ldc;
             const int64_t uoff = a.rng.ld * s;
-            if (s == a.step0 || s % a.steps_per_hour == 0) {   // a new hour: its p_drive and rowzero columns
-                __syncthreads();
-                if (a.pd_smem) for (int x = tid; x < Ni; x += THREADS) pd_s[x] = pd_t[x];
-                for (int x = tid; x < Ni; x += THREADS) rz_s[x] = a.rowzero[hour * N + x];
+            const uint8_t *__restrict__ rz_t = a.rowzero + hour * N;
+            if (staged) {
+                if (s == a.step0 || s % a.steps_per_hour == 0) {   // a new hour: its p_drive and rowzero columns
+                    __syncthreads();
+                    if (a.pd_smem) for (int x = tid; x < Ni; x += THREADS) pd_s[x] = pd_t[x];
+                    for (int x = tid; x < Ni; x += THREADS) rz_s[x] = rz_t[x];
+                }
+                __syncthreads();   // columns loaded; the previous step's flush is done with the histograms
             }
-            __syncthreads();   // columns loaded; the previous step's flush is done with the histograms
 
             uint32_t dq_head = 0, fq_head = 0;
             int dq_cnt = 0, fq_cnt = 0;
@@ -149,28 +158,28 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                 }
                 // first index in [lo, last] whose CDF value is not below u2 (NaN counts as not below, like the binary search
                 // of the other samplers: the row is non-decreasing with a NaN tail, so the predicate is monotone and the
-                // answer is the same index).  The guide leaves a window of a few entries: four independent loads per trip
+                // answer is the same index).  The guide leaves a window of a few entries: eight independent loads per trip
                 // and entry instead of a chain of dependent probes.
                 bool more;
                 do {
-                    double r[E][4];
+                    double r[E][W];
 #pragma unroll
                     for (int e = 0; e < E; ++e)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) r[e][q] = (lo[e] + q <= last[e]) ? __ldg(row[e] + lo[e] + q) : CUDART_INF;
+                        for (int q = 0; q < W; ++q) r[e][q] = (lo[e] + q <= last[e]) ? __ldg(row[e] + lo[e] + q) : CUDART_INF;
                     more = false;
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         if (lo[e] <= last[e]) {
-                            int q = 4;
+                            int q = W;
                             double v = 0.0;
 #pragma unroll
-                            for (int k = 3; k >= 0; --k) if (!(r[e][k] < u2[e])) { q = k; v = r[e][k]; }
-                            if (q < 4) {
+                            for (int k = W - 1; k >= 0; --k) if (!(r[e][k] < u2[e])) { q = k; v = r[e][k]; }
+                            if (q < W) {
                                 if (lo[e] + q <= last[e] && u2[e] <= v) dest[e] = lo[e] + q + 1;   // else 0: lost (:32,40)
                                 lo[e] = last[e] + 1;   // done
                             } else {
-                                lo[e] += 4;
+                                lo[e] += W;
                                 more |= lo[e] <= last[e];
                             }
                         }
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                 for (int j = 0; j < U; ++j) {
                     const bool parked = z[j] != 0 && z[j] != kNoCar;
                     if (!a.counts) lost += z[j] == 0;   // without the per-step rows the lost-car visits are counted here
-                    pdz[j] = !parked ? -1.0 : (a.pd_smem ? pd_s[z[j] - 1] : __ldg(pd_t + (z[j] - 1)));   // -1: never drives
+                    pdz[j] = !parked ? -1.0 : (staged && a.pd_smem ? pd_s[z[j] - 1] : __ldg(pd_t + (z[j] - 1)));   // -1: never drives
                 }
                 bool srch[U];
                 unsigned long long uq[U];
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                     srch[j] = false;
                     if (drive) {
                         if (a.counts) atomicAdd(&hdrv[(z[j] - 1) >> 1], 1u << (((z[j] - 1) & 1) * 16));   // src/saveresults.jl:13-15
-                        if (rz_s[z[j] - 1]) { if (TIME) t_hi += 300ull; }             // all-zero row: stays, 5 min (:35-36, :58-59)
+                        if (staged ? rz_s[z[j] - 1] : __ldg(rz_t + (z[j] - 1))) { if (TIME) t_hi += 300ull; }             // all-zero row: stays, 5 min (:35-36, :58-59)
                         else srch[j] = true;
                     }
                 }
