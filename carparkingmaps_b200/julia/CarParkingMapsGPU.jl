@@ -20,7 +20,7 @@ module CarParkingMapsGPU
 
 export createpdrive, createpdestin, initializestates, solveinitialvalueproblem, resampling,
        averagedrivingtime, correctparameters, zonehistogram, sampledataset, sampledatasetrows, polygoncentroids,
-       distancematrix, cpm_seed!, pin!, unpin!, pinned_zeros, inputcache!, sampledatasets, splitcity
+       distancematrix, cpm_seed!, pin!, unpin!, pinned_zeros, inputcache!, graphs!, sampledatasets, splitcity
 
 const LIBCPM = get(ENV, "LIBCPM", joinpath(@__DIR__, "..", "libcpm.so"))
 
@@ -248,6 +248,10 @@ end
 # arrays and skips the upload when a later call passes the same unchanged array (main.jl:82-98 passes datamatrix three
 # times and p_dest twice).  A host program that edits those arrays in place between calls switches that off:
 inputcache!(on::Bool) = check(ccall((:cpm_ctx_set_input_cache, LIBCPM), Int32, (Ptr{Cvoid}, Int32), ctx(), Int32(on)))
+
+# Small cities (fleets of at most 300,000 cars): from the third dataset of the same shape on, sampledataset replays its
+# launch sequence as a CUDA graph (same kernels, same results).  graphs!(false) keeps every pass on direct launches.
+graphs!(on::Bool) = check(ccall((:cpm_ctx_set_graphs, LIBCPM), Int32, (Ptr{Cvoid}, Int32), ctx(), Int32(on)))
 
 # ---------------------------------------------------------------------------------------------------------------------
 # several GPUs from this one Julia process
