@@ -512,7 +512,7 @@ extern "C" int32_t cpm_debug_cars_geometry(int64_t N, int64_t C, int32_t with_ti
     ARG(out6 && N >= 1 && C >= 1);
     CarsGeom g;
     memset(&g, 0, sizeof g);
-    const bool ok = cars_geometry(N, C, with_time, &g);
+    const bool ok = cars_geometry(N, C, with_time, 1, &g);
     const int64_t v[6] = { ok ? 1 : 0, g.n_ctas, g.threads, g.cars_per_cta, g.pd_smem, (int64_t)g.smem };
     for (int k = 0; k < 6; ++k) out6[k] = v[k];
     return CPM_OK;
@@ -904,7 +904,7 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, boo
     const int64_t N = city->N, C = f->C, S = o->n_steps;
     const size_t NB = (size_t)N + 1;
     CarsGeom g;
-    if (!cars_geometry(N, C, o->with_time, &g)) return fail(CPM_ERR_ARG, "the car-resident sampler does not support this city size");
+    if (!cars_geometry(N, C, o->with_time, want_counts ? 1 : 0, &g)) return fail(CPM_ERR_ARG, "the car-resident sampler does not support this city size");
     if (!f->zone_valid) return fail(CPM_ERR_STATE, "fleet zones are not materialised");
     if (want_counts) {
         TRY(f->cars_cnt.ensure((2 * (size_t)S + 1) * NB * 4));
@@ -954,7 +954,7 @@ static int32_t pick_sampler(const cpm_city *city, const cpm_fleet *f, int32_t wa
 {
     if (traj || want == CPM_SAMPLER_GATHER || city->G <= 0) return CPM_SAMPLER_GATHER;
     CarsGeom g;
-    const bool cars = cars_geometry(city->N, f->C, with_time, &g), bucket = bucket_supported(city->N, city->ldc);
+    const bool cars = cars_geometry(city->N, f->C, with_time, 1, &g), bucket = bucket_supported(city->N, city->ldc);
     if (want == CPM_SAMPLER_CARS) return cars ? CPM_SAMPLER_CARS : -1;
     if (want == CPM_SAMPLER_BUCKET) return bucket ? CPM_SAMPLER_BUCKET : -1;
     static const int prefer_bucket = getenv("CPM_PREFER_BUCKET") ? atoi(getenv("CPM_PREFER_BUCKET")) : 0;

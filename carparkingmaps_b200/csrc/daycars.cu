@@ -39,12 +39,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
     // shared memory: drive queues | far queues | p_drive column | net arrivals | drivers | rowzero column | zones
     unsigned long long *const dq = reinterpret_cast<unsigned long long *>(smem_raw) + wid * kCarQueue;
     unsigned long long *const fq = reinterpret_cast<unsigned long long *>(smem_raw) + (WARPS + wid) * kCarQueue;
+    // (the per-zone tables only exist when the day keeps per-step rows: a.counts)
     double *const pd_s = reinterpret_cast<double *>(smem_raw) + (TIME ? 2 : 1) * WARPS * kCarQueue;
-    uint32_t *const hnet = reinterpret_cast<uint32_t *>(pd_s + (a.pd_smem ? N : 0));
-    uint32_t *const hdrv = hnet + NB;                 // two 16-bit counters per word: a CTA holds fewer than 65,536 cars
-    const int NW = (NB + 1) >> 1;                     // words of hdrv
-    uint8_t *const rz_s = reinterpret_cast<uint8_t *>(hdrv + NW);
-    uint16_t *const zs = reinterpret_cast<uint16_t *>(rz_s + ((N + 3) & ~(int64_t)3));
+    uint32_t *const hnet = reinterpret_cast<uint32_t *>(pd_s + (a.counts && a.pd_smem ? N : 0));
+    uint32_t *const hdrv = hnet + (a.counts ? NB : 0);   // two 16-bit counters per word: a CTA holds fewer than 65,536 cars
+    const int NW = (NB + 1) >> 1;                        // words of hdrv
+    uint8_t *const rz_s = reinterpret_cast<uint8_t *>(hdrv + (a.counts ? NW : 0));
+    uint16_t *const zs = reinterpret_cast<uint16_t *>(rz_s + (a.counts ? ((N + 3) & ~(int64_t)3) : 0));
     const int cpc = a.cars_per_cta, spw = cpc / WARPS;   // slots per CTA / per warp (spw: a multiple of 32)
     const int wbase = wid * spw;
     // With per-step rows the warps of a CTA meet at every step anyway, so the hour's p_drive / rowzero columns are staged in
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
         const int n_cars = (int)((C - base < cpc) ? (C - base) : cpc);
         const int64_t car0 = base + wbase;   // the warp's first car
         __syncthreads();
-        for (int x = tid; x < NB + NW; x += THREADS) hnet[x] = 0u;   // hnet and hdrv are adjacent
+        if (a.counts) for (int x = tid; x < NB + NW; x += THREADS) hnet[x] = 0u;   // hnet and hdrv are adjacent
         __syncthreads();
         // the CTA's cars: zones into shared memory, and their share of the occupancy at the first step
         for (int x = tid; x < cpc; x += THREADS) {
@@ -320,17 +321,17 @@ __global__ void __launch_bounds__(256) k_cars_export_counts(const uint32_t *__re
 // ------------------------------------------------------------------------------------------------
 // geometry and launchers
 // ------------------------------------------------------------------------------------------------
-bool cars_geometry(int64_t N, int64_t C, int with_time, CarsGeom *g)
+bool cars_geometry(int64_t N, int64_t C, int with_time, int counts, CarsGeom *g)
 {
     if (N < 1 || N + 1 > 65535 || C < 1) return false;
     const int threads = kCarThreads, per_sm = 1, warps = threads / 32;
     const size_t cap = (size_t)(232448 - 1024 * per_sm) / per_sm - 64;   // opt-in maximum per SM minus the per-CTA reserve
     const size_t queues = (size_t)warps * kCarQueue * 8 * (with_time ? 2 : 1);
-    const size_t hist = (size_t)(N + 1) * 4 + (size_t)((N + 2) / 2) * 4 + (size_t)((N + 3) & ~(int64_t)3);   // hnet, hdrv (16-bit), rowzero
+    const size_t hist = counts ? (size_t)(N + 1) * 4 + (size_t)((N + 2) / 2) * 4 + (size_t)((N + 3) & ~(int64_t)3) : 0;   // hnet, hdrv (16-bit), rowzero
     const int64_t n_ctas = (int64_t)kSMs * per_sm;
     const int64_t want = ((C + n_ctas - 1) / n_ctas + threads - 1) / threads * threads;   // every warp owns a multiple of 32 slots
     for (int pd_smem = 1; pd_smem >= 0; --pd_smem) {
-        const size_t fixed = queues + hist + (pd_smem ? (size_t)N * 8 : 0) + 32;
+        const size_t fixed = queues + hist + (pd_smem && counts ? (size_t)N * 8 : 0) + 32;
         if (fixed + (size_t)threads * 2 > cap) continue;
         int64_t cpc = (int64_t)((cap - fixed) / 2);
         cpc = cpc / threads * threads;
@@ -369,8 +370,9 @@ static int day_cars_launch_u(const DayArgs &a, const CarsGeom &g, cudaStream_t s
 
 int launch_day_cars(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
 {
-    // one CTA of 1,024 threads per SM, two cars per lane and trip.  Measured at cfg2 (profiles/README.md): 2 x 512 and
-    // 2 x 768 threads per SM 45 % / 95 % slower per step, four cars per lane 11 % slower, one car per lane 2 % slower.
+    // one CTA of 1,024 threads per SM, two cars per lane and trip.  Measured at cfg2 (profiles/README.md): 2 x 512 threads
+    // per SM 45 % slower per step, 2 x 768 for the IVP day (40 registers, spills) 17 % slower, four cars per lane 11 %
+    // slower, one car per lane 2 % slower.
     constexpr int T = kCarThreads, U = 2;
     const bool inj = a.rng.mode == 1, time = a.with_time != 0;
     if (inj) return time ? day_cars_launch_u<T, true, true, U>(a, g, st) : day_cars_launch_u<T, true, false, U>(a, g, st);

@@ -85,7 +85,7 @@ struct DayArgs {
     RngDev rng;
     unsigned long long *t_hi, *t_lo;
 };
-bool cars_geometry(int64_t N, int64_t C, int with_time, CarsGeom *g);
+bool cars_geometry(int64_t N, int64_t C, int with_time, int counts, CarsGeom *g);
 int launch_day_cars(const DayArgs &a, const CarsGeom &g, cudaStream_t st);
 int launch_cars_export_counts(const uint32_t *cnt0, const uint32_t *net, const uint32_t *drv, int N, int64_t n_steps,
                               uint32_t *parking, uint32_t *driving, unsigned long long *lost, cudaStream_t st);
