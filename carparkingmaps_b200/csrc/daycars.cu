@@ -339,6 +339,11 @@ bool cars_geometry(int64_t N, int64_t C, int with_time, int counts, CarsGeom *g)
         if (cpc > (int64_t)4096 * warps) cpc = (int64_t)4096 * warps;   // 12-bit slot numbers inside a warp
         if (cpc > 65535 / threads * threads) cpc = 65535 / threads * threads;   // 16-bit driver counters per CTA and bin
         if (cpc < threads) continue;
+        if (cpc < want) {   // several blocks of cars per CTA: size them so that every CTA walks the same number
+            const int64_t waves = (C + cpc * n_ctas - 1) / (cpc * n_ctas);
+            const int64_t even = ((C + waves * n_ctas - 1) / (waves * n_ctas) + threads - 1) / threads * threads;
+            if (even < cpc) cpc = even;
+        }
         g->threads = threads; g->pd_smem = pd_smem; g->cars_per_cta = (int)cpc;
         const int64_t need = (C + cpc - 1) / cpc;
         g->n_ctas = (int)(need < n_ctas ? need : n_ctas);

@@ -109,3 +109,13 @@ def test_cars_any_city_size(N, cpz, with_time):
 @given(st.integers(1, 5000), st.integers(1, 2**31 - 1), st.booleans())
 def test_cars_any_fleet_size(N, cars, with_time):
     check_cars(N, cars, with_time)
+
+
+def test_cars_blocks_are_balanced_over_the_ctas():
+    """A fleet that needs several blocks of cars per CTA (cfg5: 10^4 zones, 12.5 M cars per GPU) is cut so that every CTA
+    walks the same number of blocks (within one)."""
+    g = cars_geom(10000, 12_500_000, 1)
+    blocks = -(-12_500_000 // g["cars_per_cta"])
+    waves = -(-blocks // 148)
+    assert g["n_ctas"] == 148 and blocks > 148
+    assert blocks > (waves - 1) * 148 + 148 * 0.9          # the last wave is at least 90 % full

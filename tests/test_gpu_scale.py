@@ -108,3 +108,27 @@ def test_cfg5_table_shape_small_fleet(ctx):
     e = h.counts() + (h.zones(),)
     assert np.array_equal(b[0], e[0]) and np.array_equal(b[1], e[1]) and b[2] == e[2] and np.array_equal(b[4], e[4])
     f.close(); g.close(); h.close(); city.close()
+
+
+def test_cars_sampler_several_blocks_per_cta(ctx):
+    """A fleet too large for one block of cars per CTA (10^4 zones leave room for ~24 K cars in shared memory; 6 M cars =
+    293 blocks over 148 CTAs): the car-resident kernel walks its blocks one after the other, each through the whole
+    day.  Must equal the bucket sampler bit for bit, and a split run with global car offsets."""
+    N, cpz, sph = 10000, 600, 2
+    C = N * cpz
+    city = City(ctx, N, 4).synth(seed=2, density=0.05).build_pdrive(0.1, 0.9, 0.5).build_pdestin(2, keep_p_dest=False)
+    out = {}
+    for sampler in (SAMPLER_BUCKET, SAMPLER_CARS):
+        f = Fleet(ctx, C).init(cpz)
+        f.run_day(city, 3 * sph, with_time=True, steps_per_hour=sph, sampler=sampler, rng=Rng(seed=3, stream=1))
+        out[sampler] = f.counts() + (f.zones(),)
+        f.close()
+    a, b = out[SAMPLER_BUCKET], out[SAMPLER_CARS]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+    assert np.array_equal(a[4], b[4]) and (b[0].sum(axis=0) == C).all()
+    h = C // 3 + 777
+    p = _day(ctx, city, h, cpz, SAMPLER_CARS, seed=3, n_steps=3, car_offset=0)
+    q = _day(ctx, city, C - h, cpz, SAMPLER_CARS, seed=3, n_steps=3, car_offset=h)
+    whole = _day(ctx, city, C, cpz, SAMPLER_CARS, seed=3, n_steps=3)
+    assert np.array_equal(p[0] + q[0], whole[0]) and np.array_equal(p[1] + q[1], whole[1])
+    city.close()
