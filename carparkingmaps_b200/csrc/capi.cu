@@ -505,16 +505,16 @@ extern "C" int32_t cpm_debug_bucket_geometry(int64_t N, int64_t C, int32_t with_
     return CPM_OK;
 }
 
-// The same for the car-resident day kernel (csrc/daycars.cu): out6 = {supported, CTAs, threads, car slots per CTA,
-// p_drive column staged in shared memory, bytes of shared memory}.
-extern "C" int32_t cpm_debug_cars_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out6)
+// The same for the car-resident day kernel (csrc/daycars.cu): out5 = {supported, CTAs, threads, car slots per CTA,
+// bytes of shared memory}.
+extern "C" int32_t cpm_debug_cars_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out5)
 {
-    ARG(out6 && N >= 1 && C >= 1);
+    ARG(out5 && N >= 1 && C >= 1);
     CarsGeom g;
     memset(&g, 0, sizeof g);
     const bool ok = cars_geometry(N, C, with_time, 1, &g);
-    const int64_t v[6] = { ok ? 1 : 0, g.n_ctas, g.threads, g.cars_per_cta, g.pd_smem, (int64_t)g.smem };
-    for (int k = 0; k < 6; ++k) out6[k] = v[k];
+    const int64_t v[5] = { ok ? 1 : 0, g.n_ctas, g.threads, g.cars_per_cta, (int64_t)g.smem };
+    for (int k = 0; k < 5; ++k) out5[k] = v[k];
     return CPM_OK;
 }
 
@@ -918,7 +918,7 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, boo
     a.rowzero = city->rowzero.as<uint8_t>(); a.dm = city->dm.as<double>();
     a.msd = city->have_msd ? city->msd.as<double2>() : nullptr;
     a.N = N; a.T_tab = city->T; a.C = C; a.steps_per_hour = o->steps_per_hour; a.with_time = o->with_time;
-    a.pd_smem = g.pd_smem; a.cars_per_cta = g.cars_per_cta;
+    a.cars_per_cta = g.cars_per_cta;
     a.zone = f->zone.as<int32_t>();
     a.counts = want_counts ? 1 : 0;
     if (want_counts) { a.cnt0 = f->cars_cnt.as<uint32_t>(); a.net = a.cnt0 + NB; a.drv = a.net + (size_t)S * NB; }

@@ -5,7 +5,7 @@
 // global car id and step), and the per-zone counts are sums.  So a CTA takes a contiguous block of cars, keeps their
 // zones in shared memory (16 bits per car) for the whole day and walks the steps on its own -- no sort, no exchange, no
 // kernel boundary between steps.  Per step a warp
-//   1. decides for each of its cars whether it drives (one Philox block, the hour's p_drive column from shared memory),
+//   1. decides for each of its cars whether it drives (one Philox block against the hour's p_drive column),
 //   2. queues the drivers and serves them in dense batches of 32: guide cell -> a window of a few CDF entries of the
 //      origin's row (global memory) -> destination,
 //   3. queues the cars that changed zone and draws their travel times in dense batches (resampling day only).
@@ -36,22 +36,22 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
     const int Ni = (int)N, NB = Ni + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    // shared memory: drive queues | far queues | p_drive column | net arrivals | drivers | rowzero column | zones
+    // shared memory: drive queues | far queues | net arrivals | drivers | rowzero column | zones
     unsigned long long *const dq = reinterpret_cast<unsigned long long *>(smem_raw) + wid * kCarQueue;
     unsigned long long *const fq = reinterpret_cast<unsigned long long *>(smem_raw) + (WARPS + wid) * kCarQueue;
     // (the per-zone tables only exist when the day keeps per-step rows: a.counts)
-    double *const pd_s = reinterpret_cast<double *>(smem_raw) + (TIME ? 2 : 1) * WARPS * kCarQueue;
-    uint32_t *const hnet = reinterpret_cast<uint32_t *>(pd_s + (a.counts && a.pd_smem ? N : 0));
+    uint32_t *const hnet = reinterpret_cast<uint32_t *>(smem_raw) + 2 * (TIME ? 2 : 1) * WARPS * kCarQueue;
     uint32_t *const hdrv = hnet + (a.counts ? NB : 0);   // two 16-bit counters per word: a CTA holds fewer than 65,536 cars
     const int NW = (NB + 1) >> 1;                        // words of hdrv
     uint8_t *const rz_s = reinterpret_cast<uint8_t *>(hdrv + (a.counts ? NW : 0));
     uint16_t *const zs = reinterpret_cast<uint16_t *>(rz_s + (a.counts ? ((N + 3) & ~(int64_t)3) : 0));
     const int cpc = a.cars_per_cta, spw = cpc / WARPS;   // slots per CTA / per warp (spw: a multiple of 32)
     const int wbase = wid * spw;
-    // With per-step rows the warps of a CTA meet at every step anyway, so the hour's p_drive / rowzero columns are staged in
-    // shared memory; without (the IVP of a dataset pass) the warps run through the day without a single block barrier and
-    // read the two columns through L1.
-    const bool staged = a.counts != 0;   // (staging without rows: +2 % per step at cfg2)
+    // With per-step rows the warps of a CTA meet at every step anyway, so the hour's rowzero column is staged in shared
+    // memory; without (the IVP of a dataset pass) the warps run through the day without a single block barrier.  The
+    // p_drive column is read through L1 either way (staged: +1 % per step at cfg2, and at 10^4 zones its 80 KB halve the
+    // block of cars a CTA can hold: +35 % per step).
+    const bool staged = a.counts != 0;
     unsigned long long t_hi = 0ull, t_lo = 0ull, lost = 0ull;
     if (tid < 3) red[tid] = 0ull;
 
@@ -86,12 +86,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
             const int64_t uoff = a.rng.ld * s;
             const uint8_t *__restrict__ rz_t = a.rowzero + hour * N;
             if (staged) {
-                if (s == a.step0 || s % a.steps_per_hour == 0) {   // a new hour: its p_drive and rowzero columns
+                if (s == a.step0 || s % a.steps_per_hour == 0) {   // a new hour: its rowzero column
                     __syncthreads();
-                    if (a.pd_smem) for (int x = tid; x < Ni; x += THREADS) pd_s[x] = pd_t[x];
                     for (int x = tid; x < Ni; x += THREADS) rz_s[x] = rz_t[x];
                 }
-                __syncthreads();   // columns loaded; the previous step's flush is done with the histograms
+                __syncthreads();   // column loaded; the previous step's flush is done with the histograms
             }
 
             uint32_t dq_head = 0, fq_head = 0;
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                 for (int j = 0; j < U; ++j) {
                     const bool parked = z[j] != 0 && z[j] != kNoCar;
                     if (!a.counts) lost += z[j] == 0;   // without the per-step rows the lost-car visits are counted here
-                    pdz[j] = !parked ? -1.0 : (staged && a.pd_smem ? pd_s[z[j] - 1] : __ldg(pd_t + (z[j] - 1)));   // -1: never drives
+                    pdz[j] = !parked ? -1.0 : __ldg(pd_t + (z[j] - 1));   // -1: never drives
                 }
                 bool srch[U];
                 unsigned long long uq[U];
@@ -330,27 +329,23 @@ bool cars_geometry(int64_t N, int64_t C, int with_time, int counts, CarsGeom *g)
     const size_t hist = counts ? (size_t)(N + 1) * 4 + (size_t)((N + 2) / 2) * 4 + (size_t)((N + 3) & ~(int64_t)3) : 0;   // hnet, hdrv (16-bit), rowzero
     const int64_t n_ctas = (int64_t)kSMs * per_sm;
     const int64_t want = ((C + n_ctas - 1) / n_ctas + threads - 1) / threads * threads;   // every warp owns a multiple of 32 slots
-    for (int pd_smem = 1; pd_smem >= 0; --pd_smem) {
-        const size_t fixed = queues + hist + (pd_smem && counts ? (size_t)N * 8 : 0) + 32;
-        if (fixed + (size_t)threads * 2 > cap) continue;
-        int64_t cpc = (int64_t)((cap - fixed) / 2);
-        cpc = cpc / threads * threads;
-        if (cpc > want) cpc = want;
-        if (cpc > (int64_t)4096 * warps) cpc = (int64_t)4096 * warps;   // 12-bit slot numbers inside a warp
-        if (cpc > 65535 / threads * threads) cpc = 65535 / threads * threads;   // 16-bit driver counters per CTA and bin
-        if (cpc < threads) continue;
-        if (cpc < want) {   // several blocks of cars per CTA: size them so that every CTA walks the same number
-            const int64_t waves = (C + cpc * n_ctas - 1) / (cpc * n_ctas);
-            const int64_t even = ((C + waves * n_ctas - 1) / (waves * n_ctas) + threads - 1) / threads * threads;
-            if (even < cpc) cpc = even;
-        }
-        g->threads = threads; g->pd_smem = pd_smem; g->cars_per_cta = (int)cpc;
-        const int64_t need = (C + cpc - 1) / cpc;
-        g->n_ctas = (int)(need < n_ctas ? need : n_ctas);
-        g->smem = fixed + (size_t)cpc * 2;
-        return true;
+    const size_t fixed = queues + hist + 32;
+    if (fixed + (size_t)threads * 2 > cap) return false;
+    int64_t cpc = (int64_t)((cap - fixed) / 2);
+    cpc = cpc / threads * threads;
+    if (cpc > want) cpc = want;
+    if (cpc > (int64_t)4096 * warps) cpc = (int64_t)4096 * warps;   // 12-bit slot numbers inside a warp
+    if (cpc > 65535 / threads * threads) cpc = 65535 / threads * threads;   // 16-bit driver counters per CTA and bin
+    if (cpc < want) {   // several blocks of cars per CTA: size them so that every CTA walks the same number
+        const int64_t waves = (C + cpc * n_ctas - 1) / (cpc * n_ctas);
+        const int64_t even = ((C + waves * n_ctas - 1) / (waves * n_ctas) + threads - 1) / threads * threads;
+        if (even < cpc) cpc = even;
     }
-    return false;
+    g->threads = threads; g->cars_per_cta = (int)cpc;
+    const int64_t need = (C + cpc - 1) / cpc;
+    g->n_ctas = (int)(need < n_ctas ? need : n_ctas);
+    g->smem = fixed + (size_t)cpc * 2;
+    return true;
 }
 
 template <int THREADS, bool INJ, bool TIME, int U>

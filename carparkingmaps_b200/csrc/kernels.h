@@ -67,7 +67,6 @@ int launch_reduce_partials(const double *partials, int n, double *out, cudaStrea
 struct CarsGeom {
     int n_ctas, threads;
     int cars_per_cta;          // car slots a CTA keeps in shared memory (a multiple of threads)
-    int pd_smem;               // the hour's p_drive column is staged in shared memory
     size_t smem;
 };
 struct DayArgs {
@@ -75,7 +74,7 @@ struct DayArgs {
     const double2 *msd;        // nullable: (mean, std) pairs
     int64_t N, T_tab, C;
     int64_t step0, n_steps, steps_per_hour;
-    int32_t with_time, pd_smem, cars_per_cta;
+    int32_t with_time, cars_per_cta;
     int32_t counts;            // 0: no per-zone counts (cnt0 / net / drv unused); the lost-car visits go to lost_visits
     int32_t *zone;             // [C] in/out: 1-based zone, 0 = lost
     uint32_t *cnt0;            // nullable: [N+1] += occupancy of every bin before step0 (bin N = lost cars)

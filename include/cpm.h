@@ -284,9 +284,9 @@ int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64_t C, const
  * out8 = {supported, slabs (CTAs), slots per slab, threads per CTA, CDF row buffers, bytes of shared memory of the
  * sampling kernel, of the scatter kernel, doubles per CDF row block}. */
 int32_t cpm_debug_bucket_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out8);
-/* The same for the car-resident day kernel (CPM_SAMPLER_CARS): out6 = {supported, CTAs, threads per CTA, car slots a CTA
- * keeps in shared memory, 1 if the hour's p_drive column is staged in shared memory, bytes of shared memory}. */
-int32_t cpm_debug_cars_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out6);
+/* The same for the car-resident day kernel (CPM_SAMPLER_CARS): out5 = {supported, CTAs, threads per CTA, car slots a CTA
+ * keeps in shared memory, bytes of shared memory}. */
+int32_t cpm_debug_cars_geometry(int64_t N, int64_t C, int32_t with_time, int64_t *out5);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Several GPUs from one host process                                                       */

@@ -65,9 +65,9 @@ def test_too_many_zones_fall_back():
 
 # ---- the car-resident day kernel (csrc/daycars.cu cars_geometry) ------------------------------------------------------
 def cars_geom(N, cars, with_time):
-    out = (C.c_int64 * 6)()
+    out = (C.c_int64 * 5)()
     L.check(L.lib().cpm_debug_cars_geometry(int(N), int(cars), int(with_time), out))
-    return dict(zip(("supported", "n_ctas", "threads", "cars_per_cta", "pd_smem", "smem"), list(out)))
+    return dict(zip(("supported", "n_ctas", "threads", "cars_per_cta", "smem"), list(out)))
 
 
 def check_cars(N, cars, with_time):
@@ -81,7 +81,7 @@ def check_cars(N, cars, with_time):
     assert cpc // 32 <= 4096                      # 12-bit slot numbers inside a warp
     assert cpc <= 65535                           # 16-bit driver counters per CTA and bin
     assert g["smem"] <= SMEM_CAP - 1024
-    tables = (N + 1) * 4 + (N + 2) // 2 * 4 + N + (8 * N if g["pd_smem"] else 0)
+    tables = (N + 1) * 4 + (N + 2) // 2 * 4 + N
     assert g["smem"] >= tables + 2 * cpc + 32 * 64 * 8 * (2 if with_time else 1)
     # every car is covered: a CTA walks blocks of cars_per_cta cars with stride n_ctas
     assert g["n_ctas"] * cpc >= cars or g["n_ctas"] == 148
@@ -96,7 +96,7 @@ def test_cars_named_configs(N, cpz):
         assert check_cars(N, N * cpz, wt)["supported"]
     if (N, cpz) == (2400, 1000):
         g = cars_geom(N, N * cpz, 1)
-        assert g["cars_per_cta"] == 16384 and g["n_ctas"] == 147 and g["pd_smem"] == 1
+        assert g["cars_per_cta"] == 16384 and g["n_ctas"] == 147
 
 
 @settings(max_examples=300, deadline=None)
