@@ -99,3 +99,24 @@ def test_sweep_sets_replay_and_match(ctx):
     for w, g in zip(want, got):
         np.testing.assert_array_equal(w, g)
     city.close()
+
+
+def test_auto_resolves_to_the_day_kernel_and_says_so(ctx):
+    """CPM_SAMPLER_AUTO runs a day on the car-resident kernel wherever its tables fit shared memory; a forced sampler is
+    what runs; cpm_fleet_last_sampler reports it (bench.py names the kernel it timed from this)."""
+    from carparkingmaps_b200 import SAMPLER_BUCKET, SAMPLER_CARS, SAMPLER_GATHER, Rng
+    N, cpz = 33, 20
+    city = City(ctx, N, T).synth(seed=1, density=1.0)
+    fleet = Fleet(ctx, N * cpz)
+    sample_dataset(city, fleet, cars_per_zone=cpz, seed=1)
+    assert fleet.last_sampler == SAMPLER_CARS
+    ref = None
+    for want in (SAMPLER_BUCKET, SAMPLER_GATHER, SAMPLER_CARS):
+        fleet.init(cpz).run_day(city, 5, with_time=True, sampler=want, rng=Rng(seed=2, stream=1))
+        assert fleet.last_sampler == want
+        got = fleet.counts()
+        if ref is not None:
+            np.testing.assert_array_equal(got[0], ref[0]); np.testing.assert_array_equal(got[1], ref[1])
+            assert got[2] == ref[2] and got[3] == ref[3]
+        ref = got
+    fleet.close(); city.close()
