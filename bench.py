@@ -376,9 +376,9 @@ def bench_cfg5(ctx, tm, rank, world, torch, dist_, N, cars_per_rank, n_steps, sp
 
 
 def bench_small_city(ctx, tm, T, passes=40, sets=64):
-    """BASELINE configs[0] (the reference's own CPU-runnable case: 100 zones x 1,000 cars): a pass is ~110 launches of
-    kernels that take a few microseconds each, so the host's launch rate bounds it.  Timed with direct launches and with
-    the pass replayed as a CUDA graph (cpm.h: cpm_ctx_set_graphs); results compared bit for bit.  Same for a 64-set sweep."""
+    """BASELINE configs[0] (the reference's own CPU-runnable case: 100 zones x 1,000 cars): a pass is 13 launches of
+    kernels that take a few microseconds each.  Timed with direct launches and with the pass replayed as a CUDA graph
+    (cpm.h: cpm_ctx_set_graphs); results compared bit for bit.  Same for a 64-set sweep."""
     from carparkingmaps_b200 import City, Fleet, sample_dataset, sweep
     N, cpz, _ = WORKLOADS["cfg1"]
     city = City(ctx, N, T).synth(seed=5, density=1.0)

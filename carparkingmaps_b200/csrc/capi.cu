@@ -1049,13 +1049,15 @@ extern "C" int32_t cpm_fleet_counts_device(cpm_fleet *f, void **dev_ptr, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Small cities: a pass is ~110 launches of kernels that take 2-4 us each, so the host's launch rate (4-5 us per launch)
-// sets the pace, not the GPU.  graph_run captures the launch sequence of `body` (everything it enqueues on the context's
-// stream and the streams forked from it) and replays it as one executable graph.  The first pass of a shape runs
-// directly (it allocates), the second instantiates the graph, every later one re-captures (cheap: nothing is launched)
-// and patches the executable graph's kernel arguments in place -- seeds, parameters and pointers may all differ from
-// pass to pass, only the shape of the sequence must not.  Same kernels, same arguments, same order: results are
-// identical to the direct path.  CPM_GRAPH_MAX_CARS (default 300,000; 0 = never) bounds the fleets it is used for.
+// Small cities: a pass is a short sequence of kernels that take a few microseconds each.  graph_run captures the launch
+// sequence of `body` (everything it enqueues on the context's stream and the streams forked from it) and replays it as
+// one executable graph.  The first pass of a shape runs directly (it allocates), the second instantiates the graph, every
+// later one re-captures (cheap: nothing is launched) and patches the executable graph's kernel arguments in place --
+// seeds, parameters and pointers may all differ from pass to pass, only the shape of the sequence must not.  Same kernels,
+// same arguments, same order: results are identical to the direct path.  Host cost per replayed pass: ~45 us capture,
+// ~10 us update, ~25 us launch (profiles/README.md); with the one-launch day kernel a cfg1 pass is 13 launches and
+// bound by the device's kernel-to-kernel latency, so the replay buys ~3 % there (0.37 -> 0.35 ms).
+// CPM_GRAPH_MAX_CARS (default 300,000; 0 = never) bounds the fleets it is used for.
 // ------------------------------------------------------------------------------------------------
 static int64_t graph_max_cars()
 {
@@ -1263,8 +1265,8 @@ extern "C" int32_t cpm_sample_dataset_host(cpm_city *city, cpm_fleet *fleet, con
     city_invalidate(city);
     int32_t rc;
     if (ctx->graphs && fleet->C <= graph_max_cars()) {
-        // small city: the whole upload is a few hundred microseconds, the pass is launch-bound -- wait for all of it and
-        // replay the pass as a graph (graph_run) instead of pipelining hour slabs
+        // small city: the whole upload is a few hundred microseconds -- wait for all of it and replay the pass as a graph
+        // (graph_run) instead of pipelining hour slabs
         CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[1], 0));
         rc = graph_run(fleet, pass_key(city, fleet, sampler, 1),
                        [&]() { return sample_dataset_enqueue(city, fleet, pr, cars_per_zone, seed, sampler, nullptr); });
@@ -1433,7 +1435,7 @@ extern "C" int32_t cpm_sweep(cpm_city *city, const int64_t *initial_zones, int64
         o.rng.mode = CPM_RNG_PHILOX; o.rng.seed = seed;
         o.rng.stream = streams ? streams[p] : (uint32_t)(2 + p);
         // one set = p_drive from the cached row sums, a copy of the initial state, one day, the normalisation: the same
-        // launch sequence for every set, replayed as a graph when the city is small enough to be launch-bound
+        // launch sequence for every set, replayed as a graph for small fleets (graph_run)
         if (rc == CPM_OK) rc = graph_run(work, pass_key(city, work, o.sampler, 2), [&]() -> int32_t {
             TRY(city_build_pdrive_async(city, pr.p_min, pr.p_max, pr.e_drive));   // mean_sum cached
             TRY(cpm_fleet_copy_zones(work, w->base));                             // README.md:1014,1549
