@@ -393,11 +393,12 @@ def bench_small_city(ctx, tm, T, passes=40, sets=64):
             sample_dataset(city, fleet, cars_per_zone=cpz, seed=k, **PARAMS)
         l0, r0 = ctx.launches, ctx.graph_replays
         ms, last = tm.run(lambda: [sample_dataset(city, fleet, cars_per_zone=cpz, seed=100 + k, **PARAMS) for k in range(passes)][-1])
+        kernels_per_pass = (ctx.launches - l0) / passes
         sweep(city, init, grid[:4], seed=3)
         ms_sw, sw = tm.run(lambda: sweep(city, init, grid, seed=3))
         res[name] = (last, sw)
         out[name] = {"ms_per_pass": ms / passes, "transitions_per_s": N * cpz * (2 * T - 1) * passes / (ms * 1e-3),
-                     "kernels_per_pass": (ctx.launches - l0) / passes, "graph_replays": ctx.graph_replays - r0,
+                     "kernels_per_pass": kernels_per_pass, "graph_replays": ctx.graph_replays - r0,
                      "sweep_ms_per_set": ms_sw / sets}
     ctx.set_graphs(True)
     (a, sa), (b, sb) = res["direct"], res["graph"]
