@@ -3,7 +3,8 @@
 # resampling step (launch $S2), with source correlation; exports the raw and source pages as CSV.
 out=${1:-gpurun_out/ncufull}; mkdir -p $out
 S1=${S1:-8}; S2=${S2:-31}
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-rows --no-multi --pageable-steps 1 --e2e-steps 1"
+export CPM_PREFER_BUCKET=1   # AUTO runs the car-resident day kernel; these captures are of the bucket pair
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-rows --no-multi --no-mode-j --no-small --pageable-steps 1 --e2e-steps 1"
 $CMD > $out/plain.json 2> $out/plain.err &&
 ncu --set full --clock-control none --import-source on -k regex:k_bucket_sample -s $S1 -c 1 -o $out/ivp -f $CMD > $out/ncu_ivp.log 2>&1
 $CMD > $out/plain2.json 2> $out/plain2.err &&
