@@ -61,6 +61,7 @@ SIGNATURES = {
     "cpm_ctx_uploads_skipped": (_i32, [_vp, C.POINTER(_i64)]),
     "cpm_ctx_graph_replays": (_i32, [_vp, C.POINTER(_i64)]),
     "cpm_ctx_set_graphs": (_i32, [_vp, _i32]),
+    "cpm_ctx_host_last_sampler": (_i32, [_vp, C.POINTER(_i32)]),
     "cpm_host_alloc": (_i32, [_i64, _pp]),
     "cpm_host_free": (_i32, [_vp]),
     "cpm_host_register": (_i32, [_vp, _i64]),

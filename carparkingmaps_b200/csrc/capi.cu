@@ -898,7 +898,15 @@ static int32_t day_bucket(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o)
 }
 
 // car-resident sampler: the whole day in one launch (daycars.cu); per hour when the hour's std slab is still on its way up
-static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, bool want_counts)
+// sampler of the reference-named host functions (trajectory recording): the day kernel; CPM_TRAJ_SAMPLER=1 keeps the
+// per-step gather kernel
+static int32_t host_traj_sampler()
+{
+    static const int v = getenv("CPM_TRAJ_SAMPLER") ? atoi(getenv("CPM_TRAJ_SAMPLER")) : CPM_SAMPLER_AUTO;
+    return v == CPM_SAMPLER_GATHER ? CPM_SAMPLER_GATHER : CPM_SAMPLER_AUTO;
+}
+
+static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, bool want_counts, const Traj *traj)
 {
     cpm_ctx *ctx = f->ctx;
     const int64_t N = city->N, C = f->C, S = o->n_steps;
@@ -925,6 +933,7 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, boo
     else a.lost_visits = &sc->lost;   // the scalar block was zeroed at the start of the day
     a.rng = make_rng(o->rng, C);
     a.t_hi = &sc->t_hi; a.t_lo = &sc->t_lo;
+    if (traj) { a.traj_state = traj->state; a.traj_trans = traj->trans; a.T_traj = traj->T; a.dist = city->dist.as<double>(); }
     uint32_t *const cnt0 = a.cnt0;
     const bool by_hour = ctx->step_wait != nullptr && o->with_time;
     for (int64_t s0 = 0; s0 < S;) {
@@ -952,11 +961,12 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, boo
 // the per-zone tables of the car-resident kernel do not fit shared memory, the trajectory-recording gather kernel otherwise
 static int32_t pick_sampler(const cpm_city *city, const cpm_fleet *f, int32_t want, int with_time, bool traj)
 {
-    if (traj || want == CPM_SAMPLER_GATHER || city->G <= 0) return CPM_SAMPLER_GATHER;
+    if (want == CPM_SAMPLER_GATHER || city->G <= 0) return CPM_SAMPLER_GATHER;
     CarsGeom g;
-    const bool cars = cars_geometry(city->N, f->C, with_time, 1, &g), bucket = bucket_supported(city->N, city->ldc);
+    const bool cars = cars_geometry(city->N, f->C, with_time, 1, &g), bucket = bucket_supported(city->N, city->ldc) && !traj;
     if (want == CPM_SAMPLER_CARS) return cars ? CPM_SAMPLER_CARS : -1;
     if (want == CPM_SAMPLER_BUCKET) return bucket ? CPM_SAMPLER_BUCKET : -1;
+    if (traj) return cars ? CPM_SAMPLER_CARS : CPM_SAMPLER_GATHER;   // the bucket pair does not record trajectories
     static const int prefer_bucket = getenv("CPM_PREFER_BUCKET") ? atoi(getenv("CPM_PREFER_BUCKET")) : 0;
     if (cars && !(prefer_bucket && bucket)) return CPM_SAMPLER_CARS;
     return bucket ? CPM_SAMPLER_BUCKET : CPM_SAMPLER_GATHER;
@@ -980,16 +990,15 @@ static int32_t run_day_async(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o
         if (o->with_time) ARG(o->rng.u_time && (traj == nullptr || o->rng.u_dist));
     }
     const int64_t N = city->N;
-    const int32_t sampler = (traj != nullptr && o->sampler != CPM_SAMPLER_AUTO && o->sampler != CPM_SAMPLER_GATHER)
-                                ? -1 : pick_sampler(city, f, o->sampler, o->with_time, traj != nullptr);
+    const int32_t sampler = pick_sampler(city, f, o->sampler, o->with_time, traj != nullptr);
     if (sampler < 0)
-        return fail(CPM_ERR_ARG, "the bucket and car-resident samplers need N + 1 <= 65535, per-zone tables that fit shared memory, "
-                                 "a guide table, and no trajectory recording");
+        return fail(CPM_ERR_ARG, "the bucket and car-resident samplers need N + 1 <= 65535, per-zone tables that fit shared memory and "
+                                 "a guide table; the bucket sampler does not record trajectories");
     TRY(f->counts.ensure(2 * (size_t)N * o->n_steps * sizeof(uint32_t)));
     f->counts_N = N; f->counts_steps = o->n_steps;
     CU(cudaMemsetAsync(f->scalars.p, 0, sizeof(Scalars), ctx->st));
     f->last_sampler = sampler;
-    if (sampler == CPM_SAMPLER_CARS) TRY(day_cars(city, f, o, want_counts));
+    if (sampler == CPM_SAMPLER_CARS) TRY(day_cars(city, f, o, want_counts, traj));
     else if (sampler == CPM_SAMPLER_BUCKET) TRY(day_bucket(city, f, o));
     else TRY(day_gather(city, f, o, traj));
     Scalars *sc = f->scalars.as<Scalars>();
@@ -1502,6 +1511,12 @@ extern "C" int32_t cpm_ctx_uploads_skipped(cpm_ctx *ctx, int64_t *count)
     return CPM_OK;
 }
 
+extern "C" int32_t cpm_ctx_host_last_sampler(cpm_ctx *ctx, int32_t *sampler)
+{
+    ARG(ctx && sampler);
+    *sampler = ctx->h_fleet ? ctx->h_fleet->last_sampler : 0;
+    return CPM_OK;
+}
 extern "C" int32_t cpm_ctx_set_graphs(cpm_ctx *ctx, int32_t enabled)
 {
     ARG(ctx != nullptr);
@@ -1667,7 +1682,7 @@ static int32_t host_sample(cpm_ctx *ctx, int64_t *state, double *trans, const do
     if (n_steps >= 1) {
         cpm_day_opts o;
         memset(&o, 0, sizeof o);
-        o.n_steps = n_steps; o.steps_per_hour = 1; o.with_time = ivp ? 0 : 1; o.sampler = CPM_SAMPLER_GATHER;
+        o.n_steps = n_steps; o.steps_per_hour = 1; o.with_time = ivp ? 0 : 1; o.sampler = host_traj_sampler();
         TRY(stage_rng(ctx, rng, C, n_steps, !ivp, &o.rng));
         Traj tj; tj.state = d_state; tj.trans = d_trans; tj.T = T;
         TRY(run_day_async(city, fleet, &o, &tj));

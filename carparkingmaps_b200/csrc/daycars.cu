@@ -24,7 +24,7 @@ constexpr uint16_t kNoCar = 0xFFFFu;   // slot beyond the CTA's last car
 constexpr int kCarThreads = 1024;      // one CTA per SM
 constexpr int kWindow = 8;             // CDF entries per window trip (4: +2 % per step, one more trip for half of the batches)
 
-template <int THREADS, bool INJ, bool TIME, int U>
+template <int THREADS, bool INJ, bool TIME, int U, bool TRAJ>
 __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(const DayArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,11 +98,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
             // travel times of up to 32 * E queued cars (src/resampling.jl:61-70), E per lane: the E table gathers of a lane
             // are in flight together
             auto far_batch = [&](int n) {
-                double mean[E], sd[E];
+                double mean[E], sd[E], dkm[E];
                 int64_t car[E];
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    mean[e] = sd[e] = 0.0; car[e] = 0;
+                    mean[e] = sd[e] = dkm[e] = 0.0; car[e] = 0;
                     if (lane + 32 * e < n) {
                         const unsigned long long q = fq[(fq_head + lane + 32 * e) & (kCarQueue - 1)];
                         car[e] = car0 + (int64_t)(q & 0xFFFull);
@@ -110,16 +110,23 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                         const int64_t od = (int64_t)(odp & 0xffffu) + N * (int64_t)(odp >> 16);
                         if (a.msd) { const double2 ms = __ldg(a.msd + od + NN * hour); mean[e] = ms.x; sd[e] = ms.y; }
                         else { mean[e] = __ldg(a.dm + od + NN * hour); sd[e] = __ldg(a.dm + od + NN * (hour + a.T_tab)); }
+                        if (TRAJ) dkm[e] = __ldg(a.dist + od);                        // :72
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     if (lane + 32 * e < n) {
-                        double u3;
-                        if (INJ) u3 = a.rng.u_time[car[e] + uoff];
-                        else { uint32_t o[4]; philox_words(a.rng, car[e], (uint32_t)s, 1u, o); u3 = u52(o[0], o[1]); }
+                        double u3, u4 = 0.0;
+                        if (INJ) { u3 = a.rng.u_time[car[e] + uoff]; if (TRAJ) u4 = a.rng.u_dist[car[e] + uoff]; }
+                        else { uint32_t o[4]; philox_words(a.rng, car[e], (uint32_t)s, 1u, o); u3 = u52(o[0], o[1]); if (TRAJ) u4 = u52(o[2], o[3]); }
                         if (sd[e] == 0.0) sd[e] = 0.1 * mean[e];                      // :65-67
-                        fx_add(t_hi, t_lo, truncnormal(mean[e], sd[e], u3));          // :68
+                        const double tt = truncnormal(mean[e], sd[e], u3);            // :68
+                        fx_add(t_hi, t_lo, tt);
+                        if (TRAJ) {                                                   // :69, :73-75
+                            double *tr = a.traj_trans + car[e] + C * s;
+                            tr[2 * C * a.T_traj] = tt;
+                            tr[3 * C * a.T_traj] = truncnormal(dkm[e], 0.1 * dkm[e], u4);
+                        }
                     }
                 }
             };
@@ -190,6 +197,14 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     far[e] = false; odp[e] = 0;
+                    if (TRAJ && act[e]) {   // Julia-layout trajectory of a car that drew a destination (src/resampling.jl:19-21,47,58-60,82)
+                        const int64_t car = car0 + slot[e];
+                        double *tr = a.traj_trans + car + C * s;
+                        tr[0] = 1.0;
+                        tr[C * a.T_traj] = (double)dest[e];
+                        if (TIME && dest[e] == z[e]) { tr[2 * C * a.T_traj] = 300.0; tr[3 * C * a.T_traj] = 1.0; }
+                        if (s + 1 < a.T_traj) a.traj_state[car + C * (s + 1)] = dest[e];
+                    }
                     if (act[e]) {
                         if (dest[e] != z[e]) {
                             zs[wbase + slot[e]] = (uint16_t)dest[e];                      // :81-83
@@ -243,6 +258,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2) k_day_cars(c
                         if (a.counts) atomicAdd(&hdrv[(z[j] - 1) >> 1], 1u << (((z[j] - 1) & 1) * 16));   // src/saveresults.jl:13-15
                         if (staged ? rz_s[z[j] - 1] : __ldg(rz_t + (z[j] - 1))) { if (TIME) t_hi += 300ull; }             // all-zero row: stays, 5 min (:35-36, :58-59)
                         else srch[j] = true;
+                    }
+                    if (TRAJ && z[j] != kNoCar && !srch[j]) {   // parked, lost, or driving inside an all-zero row: the car stays
+                        double *tr = a.traj_trans + car + C * s;
+                        tr[0] = drive ? 1.0 : 0.0;
+                        tr[C * a.T_traj] = (double)z[j];
+                        if (TIME && drive) { tr[2 * C * a.T_traj] = 300.0; tr[3 * C * a.T_traj] = 1.0; }
+                        if (s + 1 < a.T_traj) a.traj_state[car + C * (s + 1)] = z[j];
                     }
                 }
 #pragma unroll
@@ -348,7 +370,7 @@ bool cars_geometry(int64_t N, int64_t C, int with_time, int counts, CarsGeom *g)
     return true;
 }
 
-template <int THREADS, bool INJ, bool TIME, int U>
+template <int THREADS, bool INJ, bool TIME, int U, bool TRAJ>
 static int day_cars_launch_u(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
 {
     // the opt-in applies to the current device's copy of the kernel: once per (device, instantiation)
@@ -360,11 +382,11 @@ static int day_cars_launch_u(const DayArgs &a, const CarsGeom &g, cudaStream_t s
         std::lock_guard<std::mutex> lk(mu);
         size_t &have = granted[dev];
         if (g.smem > have) {
-            if (cudaFuncSetAttribute(k_day_cars<THREADS, INJ, TIME, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) != cudaSuccess) return -1;
+            if (cudaFuncSetAttribute(k_day_cars<THREADS, INJ, TIME, U, TRAJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem) != cudaSuccess) return -1;
             have = g.smem;
         }
     }
-    k_day_cars<THREADS, INJ, TIME, U><<<(unsigned)g.n_ctas, THREADS, g.smem, st>>>(a);
+    k_day_cars<THREADS, INJ, TIME, U, TRAJ><<<(unsigned)g.n_ctas, THREADS, g.smem, st>>>(a);
     return 1;
 }
 
@@ -375,8 +397,12 @@ int launch_day_cars(const DayArgs &a, const CarsGeom &g, cudaStream_t st)
     // slower, one car per lane 2 % slower.
     constexpr int T = kCarThreads, U = 2;
     const bool inj = a.rng.mode == 1, time = a.with_time != 0;
-    if (inj) return time ? day_cars_launch_u<T, true, true, U>(a, g, st) : day_cars_launch_u<T, true, false, U>(a, g, st);
-    return time ? day_cars_launch_u<T, false, true, U>(a, g, st) : day_cars_launch_u<T, false, false, U>(a, g, st);
+    if (a.traj_trans) {   // Julia-layout trajectories (the reference-named host functions)
+        if (inj) return time ? day_cars_launch_u<T, true, true, U, true>(a, g, st) : day_cars_launch_u<T, true, false, U, true>(a, g, st);
+        return time ? day_cars_launch_u<T, false, true, U, true>(a, g, st) : day_cars_launch_u<T, false, false, U, true>(a, g, st);
+    }
+    if (inj) return time ? day_cars_launch_u<T, true, true, U, false>(a, g, st) : day_cars_launch_u<T, true, false, U, false>(a, g, st);
+    return time ? day_cars_launch_u<T, false, true, U, false>(a, g, st) : day_cars_launch_u<T, false, false, U, false>(a, g, st);
 }
 
 int launch_cars_export_counts(const uint32_t *cnt0, const uint32_t *net, const uint32_t *drv, int N, int64_t n_steps,

@@ -81,6 +81,9 @@ struct DayArgs {
     uint32_t *net;             // [day steps][N+1] += net arrivals per bin and step (two's complement)
     uint32_t *drv;             // [day steps][N+1] += driving cars per origin and step
     unsigned long long *lost_visits;   // counts == 0 only: += cars in zone 0, summed over the steps
+    // trajectory in Julia layout (nullable; column s of the day = column s of the arrays): state Int64 [C,T_traj],
+    // trans Float64 [C,T_traj,4]; dist [N,N] feeds the distance draw that only the trajectory keeps
+    int64_t *traj_state; double *traj_trans; int64_t T_traj; const double *dist;
     RngDev rng;
     unsigned long long *t_hi, *t_lo;
 };

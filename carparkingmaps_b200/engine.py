@@ -88,6 +88,13 @@ class Context:
         L.check(L.lib().cpm_ctx_uploads_skipped(self._h, C.byref(n)))
         return n.value
 
+    @property
+    def host_last_sampler(self) -> int:
+        """Sampler of the last solveinitialvalueproblem / resampling call through the host API (SAMPLER_CARS normally)."""
+        v = C.c_int32()
+        L.check(L.lib().cpm_ctx_host_last_sampler(self._h, C.byref(v)))
+        return v.value
+
     def set_graphs(self, enabled: bool):
         """Small cities: replay repeated passes as CUDA graphs (default on)."""
         L.check(L.lib().cpm_ctx_set_graphs(self._h, int(bool(enabled))))

@@ -88,6 +88,9 @@ int32_t cpm_ctx_profile_end(cpm_ctx *ctx, double *step_kernel_ms, int64_t *step_
  * callers that edit those arrays in place between calls.  cpm_ctx_uploads_skipped counts the hits. */
 int32_t cpm_ctx_set_input_cache(cpm_ctx *ctx, int32_t enabled);
 int32_t cpm_ctx_uploads_skipped(cpm_ctx *ctx, int64_t *count);
+/* which sampler the last cpm_solve_ivp / cpm_resampling of this context ran on (CPM_SAMPLER_CARS unless the day kernel's
+ * tables do not fit shared memory; 0 before the first call) */
+int32_t cpm_ctx_host_last_sampler(cpm_ctx *ctx, int32_t *sampler);
 /* Small cities (fleets of at most CPM_GRAPH_MAX_CARS cars, default 300,000; 0 = never): from the third pass of the same
  * shape on, cpm_sample_dataset, cpm_sample_dataset_host and every set of cpm_sweep replay their launch sequence as one
  * executable CUDA graph whose kernel arguments are patched in place (same kernels, same arguments, same results; saves

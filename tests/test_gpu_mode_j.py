@@ -45,6 +45,8 @@ def test_cache_on_equals_cache_off_and_skips_uploads(ctx, N, cpz, density):
     _same(ref, got)
     # datamatrix means (createpdestin, resampling), distances (resampling), p_dest (twice), trajectory slots
     assert ctx.uploads_skipped - s0 >= 6
+    from carparkingmaps_b200 import SAMPLER_CARS
+    assert ctx.host_last_sampler == SAMPLER_CARS          # the trajectory-recording calls run on the day kernel
     # against the oracle as well (Philox, so indices are exact)
     pd = O.createpdrive(dm, dist, N, T=T, p_min=0.1, p_max=0.9, e_drive=0.5)
     px = O.createpdestin(dm, N, T=T, e_dest=2)
