@@ -764,7 +764,7 @@ static int32_t profile_close(cpm_ctx *ctx)
     return CPM_OK;
 }
 
-// gather sampler: one thread per car, car-id order (also the only path that records trajectories)
+// gather sampler: one thread per car and step, car-id order (last fallback; records trajectories too)
 static int32_t day_gather(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, const Traj *traj)
 {
     cpm_ctx *ctx = f->ctx;
@@ -958,7 +958,7 @@ static int32_t day_cars(cpm_city *city, cpm_fleet *f, const cpm_day_opts *o, boo
 }
 
 // which sampler a day runs on: the car-resident kernel wherever it applies (AUTO), the bucket pair when asked for or when
-// the per-zone tables of the car-resident kernel do not fit shared memory, the trajectory-recording gather kernel otherwise
+// the per-zone tables of the car-resident kernel do not fit shared memory, the per-step gather kernel otherwise
 static int32_t pick_sampler(const cpm_city *city, const cpm_fleet *f, int32_t want, int with_time, bool traj)
 {
     if (want == CPM_SAMPLER_GATHER || city->G <= 0) return CPM_SAMPLER_GATHER;

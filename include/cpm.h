@@ -215,9 +215,9 @@ int32_t cpm_fleet_get_zones(cpm_fleet *fleet, int64_t *zones_out);
 int32_t cpm_fleet_copy_zones(cpm_fleet *dst, const cpm_fleet *src);
 
 /* AUTO: the car-resident day kernel (CARS: one launch per day, cars stay on their SM; csrc/daycars.cu) where its per-zone
- * tables fit shared memory, else the bucket pair (BUCKET: cars re-grouped by zone every step; csrc/bucket.cu), else GATHER
- * (one thread per car and step; the only sampler that records trajectories).  Identical results: all draws are keyed by
- * global car index and step. */
+ * tables fit shared memory, else the bucket pair (BUCKET: cars re-grouped by zone every step; csrc/bucket.cu; no
+ * trajectories), else GATHER (one thread per car and step).  Identical results: all draws are keyed by global car index
+ * and step. */
 enum { CPM_SAMPLER_AUTO = 0, CPM_SAMPLER_GATHER = 1, CPM_SAMPLER_BUCKET = 2, CPM_SAMPLER_CARS = 3 };
 
 typedef struct cpm_day_opts {
